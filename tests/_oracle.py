@@ -1,0 +1,257 @@
+"""ctypes bindings for the two CPU checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+* ``Oracle``  -- oracle/_ref/libmmoracle.so, the C restatement (oracle/mm_oracle.c).
+* ``Ref``     -- oracle/_ref/libmmref.so, the UNMODIFIED reference sources compiled in
+                 place (oracle/Makefile); absent => ``Ref.available()`` is False.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+OUT_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i16p = C.POINTER(C.c_int16)
+intp = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    """Compiles oracle/ (and oracle/_ref from /root/reference when it is present)."""
+    need = force or not os.path.exists(os.path.join(OUT_DIR, "libmmoracle.so"))
+    if os.path.isdir("/root/reference/src/core") and not os.path.exists(os.path.join(OUT_DIR, "libmmref.so")):
+        need = True
+    if need:
+        subprocess.run(["make", "-C", ORACLE_DIR] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+def _u32(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
+    return a, a.ctypes.data_as(u32p)
+
+
+def codepoints(s):
+    """str / list of ints -> list of code points."""
+    if isinstance(s, str):
+        return [ord(c) for c in s]
+    return [int(c) for c in s]
+
+
+class MMError(Exception):
+    pass
+
+
+class Oracle:
+    """The C restatement.  One instance == one compiled pattern."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build()
+            lib = C.CDLL(os.path.join(OUT_DIR, "libmmoracle.so"))
+            lib.mmo_compile_keyword.restype = C.c_void_p
+            lib.mmo_compile_keyword.argtypes = [u32p, C.c_int, C.c_uint32, u32p, C.c_int, C.c_int, intp]
+            lib.mmo_compile_values.restype = C.c_void_p
+            lib.mmo_compile_values.argtypes = [i16p, C.c_int, C.c_int, intp]
+            lib.mmo_free.argtypes = [C.c_void_p]
+            lib.mmo_keyword_len.argtypes = [C.c_void_p]
+            lib.mmo_mode.argtypes = [C.c_void_p]
+            lib.mmo_search.restype = C.c_int64
+            lib.mmo_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u32p, C.c_uint64]
+            lib.mmo_table_size.argtypes = [C.c_void_p]
+            lib.mmo_table.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u32p, u32p]
+            lib.mmo_engine.restype = C.c_int64
+            lib.mmo_engine.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                       u64p, u32p, C.c_uint64]
+            lib.mmo_num_blocks.restype = C.c_uint64
+            lib.mmo_num_blocks.argtypes = [C.c_uint64, C.c_uint32]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, bits, keyword=None, wildcard=0, char_seq=(), values=None):
+        lib = self.lib()
+        self.bits = bits
+        err = C.c_int(0)
+        if values is not None:
+            v = np.ascontiguousarray(np.asarray(values, dtype=np.int16))
+            self.h = lib.mmo_compile_values(v.ctypes.data_as(i16p), len(v), bits, C.byref(err))
+        else:
+            kw, kwp = _u32(codepoints(keyword))
+            sq, sqp = _u32(codepoints(char_seq))
+            self.h = lib.mmo_compile_keyword(kwp, len(kw), int(wildcard), sqp, len(sq), bits, C.byref(err))
+        if not self.h:
+            raise MMError({1: "Skip table index out of bounds", 2: "empty keyword", 3: "non-terminating pattern",
+                           4: "bad argument"}.get(err.value, "error %d" % err.value))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib().mmo_free(self.h)
+            self.h = None
+
+    @property
+    def mode(self):
+        return self.lib().mmo_mode(self.h)
+
+    def table(self, v0, v1):
+        n = self.lib().mmo_table_size(self.h)
+        k = np.zeros(max(n, 1), np.uint32)
+        v = np.zeros(max(n, 1), np.uint32)
+        self.lib().mmo_table(self.h, int(v0), int(v1), k.ctypes.data_as(u32p), v.ctypes.data_as(u32p))
+        return {int(k[i]): int(v[i]) for i in range(n)}
+
+    def search(self, data):
+        """data: numpy array of uint8 / uint16 elements (host order).  -> (positions, vals[n,2])"""
+        data = np.ascontiguousarray(data)
+        assert data.dtype == (np.uint8 if self.bits == 8 else np.uint16)
+        n = self.lib().mmo_search(self.h, data.ctypes.data, data.size, None, None, 0)
+        pos = np.zeros(max(n, 1), np.uint64)
+        vals = np.zeros((max(n, 1), 2), np.uint32)
+        self.lib().mmo_search(self.h, data.ctypes.data, data.size, pos.ctypes.data_as(u64p),
+                              vals.ctypes.data_as(u32p), n)
+        return pos[:n], vals[:n]
+
+    def engine(self, file_bytes, block_size, big_endian=False, wrap32=True):
+        """file_bytes: numpy uint8 image of the file.  -> (offsets, vals[n,2])"""
+        fb = np.ascontiguousarray(file_bytes, dtype=np.uint8)
+        n = self.lib().mmo_engine(self.h, fb.ctypes.data, fb.size, block_size, int(big_endian), int(wrap32),
+                                  None, None, 0)
+        off = np.zeros(max(n, 1), np.uint64)
+        vals = np.zeros((max(n, 1), 2), np.uint32)
+        self.lib().mmo_engine(self.h, fb.ctypes.data, fb.size, block_size, int(big_endian), int(wrap32),
+                              off.ctypes.data_as(u64p), vals.ctypes.data_as(u32p), n)
+        return off[:n], vals[:n]
+
+
+class Ref:
+    """The unmodified reference (oracle/_ref/libmmref.so)."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        try:
+            build()
+        except Exception:
+            pass
+        return os.path.exists(os.path.join(OUT_DIR, "libmmref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build()
+            lib = C.CDLL(os.path.join(OUT_DIR, "libmmref.so"))
+            lib.ref_last_error.restype = C.c_char_p
+            sig = [C.c_int, u32p, C.c_int, C.c_uint32, u32p, C.c_int, i16p, C.c_int]
+            lib.ref_search.restype = C.c_int64
+            lib.ref_search.argtypes = sig + [C.c_void_p, C.c_uint64, u64p, u32p, u32p, u32p, C.c_uint64, C.c_uint64]
+            lib.ref_compile.restype = C.c_int
+            lib.ref_compile.argtypes = sig
+            lib.ref_time_search.restype = C.c_double
+            lib.ref_time_search.argtypes = sig + [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]
+            lib.ref_engine_run.restype = C.c_void_p
+            lib.ref_engine_run.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, u32p, C.c_int, C.c_uint32, u32p,
+                                           C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+            for f in ("ref_engine_count", "ref_engine_entries", "ref_engine_progress_count"):
+                getattr(lib, f).restype = C.c_uint64
+                getattr(lib, f).argtypes = [C.c_void_p]
+            lib.ref_engine_get.argtypes = [C.c_void_p, u64p, u32p, u32p, u32p, intp, intp]
+            lib.ref_engine_preview.restype = C.c_char_p
+            lib.ref_engine_preview.argtypes = [C.c_void_p, C.c_uint64]
+            lib.ref_engine_free.argtypes = [C.c_void_p]
+            cls._lib = lib
+        return cls._lib
+
+    @staticmethod
+    def _pattern_args(bits, keyword, wildcard, char_seq, values):
+        kw, kwp = _u32(codepoints(keyword or []))
+        sq, sqp = _u32(codepoints(char_seq or []))
+        if values is not None:
+            v = np.ascontiguousarray(np.asarray(values, dtype=np.int16))
+            vp, nv = v.ctypes.data_as(i16p), len(v)
+        else:
+            v, vp, nv = None, None, 0
+        keep = (kw, sq, v)
+        return keep, [bits, kwp, len(kw), int(wildcard), sqp, len(sq), vp, nv]
+
+    @classmethod
+    def compile_ok(cls, bits, keyword=None, wildcard=0, char_seq=(), values=None):
+        keep, args = cls._pattern_args(bits, keyword, wildcard, char_seq, values)
+        return cls.lib().ref_compile(*args) == 0
+
+    @classmethod
+    def search(cls, bits, data, keyword=None, wildcard=0, char_seq=(), values=None):
+        """-> (positions, [dict per match])"""
+        lib = cls.lib()
+        data = np.ascontiguousarray(data)
+        keep, args = cls._pattern_args(bits, keyword, wildcard, char_seq, values)
+        n = lib.ref_search(*args, data.ctypes.data, data.size, None, None, None, None, 0, 0)
+        if n < 0:
+            raise MMError(lib.ref_last_error().decode())
+        nseq = max(len(keep[1]), 2)
+        pos = np.zeros(max(n, 1), np.uint64)
+        sizes = np.zeros(max(n, 1), np.uint32)
+        keys = np.zeros(max(n * nseq, 1), np.uint32)
+        vals = np.zeros(max(n * nseq, 1), np.uint32)
+        lib.ref_search(*args, data.ctypes.data, data.size, pos.ctypes.data_as(u64p), sizes.ctypes.data_as(u32p),
+                       keys.ctypes.data_as(u32p), vals.ctypes.data_as(u32p), n, n * nseq)
+        maps, e = [], 0
+        for i in range(n):
+            maps.append({int(keys[e + j]): int(vals[e + j]) for j in range(sizes[i])})
+            e += int(sizes[i])
+        return pos[:n], maps
+
+    @classmethod
+    def time_search(cls, bits, data, iters=3, keyword=None, wildcard=0, char_seq=(), values=None):
+        lib = cls.lib()
+        data = np.ascontiguousarray(data)
+        keep, args = cls._pattern_args(bits, keyword, wildcard, char_seq, values)
+        m = C.c_int64(0)
+        t = lib.ref_time_search(*args, data.ctypes.data, data.size, iters, C.byref(m))
+        if t < 0:
+            raise MMError(lib.ref_last_error().decode())
+        return t, m.value
+
+    @classmethod
+    def engine(cls, bits, path, keyword=None, wildcard=ord("*"), char_seq=(), values=None, big_endian=False,
+               threads=1, block=524288, preview_width=50, previews=False, abort_after=0):
+        """-> dict(offsets, maps, previews, progress=[(pct, step)])"""
+        lib = cls.lib()
+        keep, args = cls._pattern_args(bits, keyword, wildcard, char_seq, values)
+        bits_, kwp, L, wc, sqp, nseq, vp, nv = args
+        if vp is None:
+            dummy = np.zeros(1, np.int16)
+            vp = dummy.ctypes.data_as(i16p)
+        h = lib.ref_engine_run(bits_, os.fsencode(path), 0 if values is not None else 1, int(big_endian), kwp, L,
+                               wc, sqp, nseq, vp, nv, threads, block, preview_width, int(previews), abort_after)
+        if not h:
+            raise MMError(lib.ref_last_error().decode())
+        try:
+            n = lib.ref_engine_count(h)
+            ne = lib.ref_engine_entries(h)
+            npg = lib.ref_engine_progress_count(h)
+            off = np.zeros(max(n, 1), np.uint64)
+            sizes = np.zeros(max(n, 1), np.uint32)
+            keys = np.zeros(max(ne, 1), np.uint32)
+            vals = np.zeros(max(ne, 1), np.uint32)
+            pct = np.zeros(max(npg, 1), np.int32)
+            step = np.zeros(max(npg, 1), np.int32)
+            lib.ref_engine_get(h, off.ctypes.data_as(u64p), sizes.ctypes.data_as(u32p), keys.ctypes.data_as(u32p),
+                               vals.ctypes.data_as(u32p), pct.ctypes.data_as(intp), step.ctypes.data_as(intp))
+            maps, e = [], 0
+            for i in range(n):
+                maps.append({int(keys[e + j]): int(vals[e + j]) for j in range(sizes[i])})
+                e += int(sizes[i])
+            previews_out = [lib.ref_engine_preview(h, i).decode("utf-8", "replace") for i in range(n)]
+            return dict(offsets=off[:n].copy(), maps=maps, previews=previews_out,
+                        progress=[(int(pct[i]), int(step[i])) for i in range(npg)])
+        finally:
+            lib.ref_engine_free(h)
