@@ -1,0 +1,133 @@
+/*
+ * mmoore_b200.h -- C-ABI of the B200-native relative-search path.
+ *
+ * This is the drop-in boundary underneath the reference's link-time C++ API
+ * (include/mmoore/{monkey_moore,search_engine}.hpp, static library monkey-core,
+ * /root/reference/src/core/CMakeLists.txt:1-3).  The reference has no FFI of its
+ * own; each entry point below names the reference interface it stands in for
+ * (file:line under /root/reference/).  The C++ classes in include/mmoore/ are thin
+ * wrappers over these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; integer status
+ * codes (0 == MMG_OK), never exceptions; the caller owns every input buffer;
+ * the library owns a results object until mmg_results_free().  Handles are
+ * immutable after creation and may be shared between threads; every scan call
+ * runs on its own CUDA stream.  There is NO CPU fallback: every scan entry
+ * point fails with MMG_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef MMOORE_B200_H
+#define MMOORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMG_OK 0
+#define MMG_ERR_SKIP_OOB 1  /* -> std::runtime_error("Skip table index out of bounds"), src/core/monkey_moore.cpp:139,274 */
+#define MMG_ERR_EMPTY 2     /* empty keyword / value list (assert at src/core/monkey_moore.cpp:18,28) */
+#define MMG_ERR_HANG 3      /* pattern whose match advance is <= 0: the reference never terminates (:398,:526); rejected */
+#define MMG_ERR_ARG 4       /* bad argument */
+#define MMG_ERR_CUDA 5      /* CUDA runtime failure or no device (message in mmg_last_error) */
+#define MMG_ERR_TOO_LONG 6  /* keyword longer than MMG_MAX_KEYWORD */
+#define MMG_ERR_NOMEM 7
+
+#define MMG_MAX_KEYWORD 128
+
+typedef struct mmg_program mmg_program;   /* a compiled pattern (== one MonkeyMoore<Ty> instance) */
+typedef struct mmg_results mmg_results;   /* the match list of one scan */
+
+/* Human-readable description of the last error on this thread. */
+const char *mmg_last_error(void);
+
+/* Number of usable CUDA devices (0 => every scan call fails with MMG_ERR_CUDA). */
+int mmg_device_count(void);
+
+/* MonkeyMoore<Ty>::MonkeyMoore(keyword, wildcard, char_seq)
+ *   include/mmoore/monkey_moore.hpp:29-33, src/core/monkey_moore.cpp:12-22, 54-304.
+ * keyword/char_seq are UTF-32 code points (CharType == char32_t); elem_bits is 8 or
+ * 16 (the two instantiations, src/core/monkey_moore.cpp:587-588). */
+int mmg_program_create_keyword(const uint32_t *keyword, int keyword_len, uint32_t wildcard,
+                               const uint32_t *char_seq, int char_seq_len, int elem_bits,
+                               mmg_program **out);
+
+/* MonkeyMoore<Ty>::MonkeyMoore(const std::vector<short>& reference_values)  (value scan)
+ *   include/mmoore/monkey_moore.hpp:40-42, src/core/monkey_moore.cpp:24-39. */
+int mmg_program_create_values(const int16_t *values, int n, int elem_bits, mmg_program **out);
+
+void mmg_program_free(mmg_program *p);
+
+/* Introspection used by the host wrappers and the tests. */
+int mmg_program_keyword_len(const mmg_program *p);
+int mmg_program_mode(const mmg_program *p);          /* 0 simple_relative, 1 wildcard_relative, 2 value_scan */
+int mmg_program_table_size(const mmg_program *p);    /* entries of the equivalency_map of a match */
+
+/* equivalency_map of one match (src/core/monkey_moore.cpp:374-393, 472-521) from the two raw
+ * element values a scan reports for it.  keys/values receive mmg_program_table_size()
+ * entries in ascending key order (std::map iteration order). */
+void mmg_program_table(const mmg_program *p, uint32_t v0, uint32_t v1, uint32_t *keys, uint32_t *values);
+
+/* Where the bytes live. */
+#define MMG_MEM_HOST 0     /* host pointer: the call copies host->device (and is what `e2e` times) */
+#define MMG_MEM_DEVICE 1   /* device pointer on the current device, 16-byte aligned */
+
+/* MonkeyMoore<Ty>::search(const Ty* data, uint64_t data_len)
+ *   include/mmoore/monkey_moore.hpp:51, src/core/monkey_moore.cpp:41-49, 316-546.
+ * data_len is in ELEMENTS, elements are in host byte order; one chain from element 0.
+ * Match positions are element indices, ascending. */
+int mmg_search(const mmg_program *p, const void *data, uint64_t data_len, int mem, mmg_results **out);
+
+/* The chunk engine of mmoore::SearchEngine<T>::run WITHOUT file I/O, previews and callbacks:
+ *   compute_search_blocks          src/core/search_engine.cpp:218-253
+ *   per-block, per-alignment scan  src/core/search_engine.cpp:129-159
+ *   merge + sort by offset         src/core/search_engine.cpp:193-197
+ * bytes/nbytes   : the file image, or the contiguous slice of it that starts at file
+ *                  offset first_block*block_size (multi-GPU sharding, one slice per rank).
+ * file_size      : size of the WHOLE file (needed to shape the last block).
+ * block_size     : SearchConfig::preferred_search_block_size.
+ * first_block,
+ * num_blocks     : which blocks of the file this call scans; the slice must cover
+ *                  [first_block*block_size, min(file_size, (first_block+num_blocks)*block_size + overlap)).
+ *                  num_blocks == 0 means "all blocks from first_block to the end".
+ * big_endian     : SearchConfig::endianness == Endianness::Big (16-bit only).
+ * Offsets reported are FILE offsets (64-bit; the reference's uint32_t wrap past 4 GiB,
+ * src/core/search_engine.cpp:241-242, is deliberately not reproduced), ascending. */
+int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem,
+                    uint64_t file_size, uint32_t block_size, uint64_t first_block, uint64_t num_blocks,
+                    int big_endian, mmg_results **out);
+
+/* Number of blocks compute_search_blocks() produces (== number of per-block progress callbacks,
+ * tests/test_search_engine.cpp:376-396). */
+uint64_t mmg_num_blocks(uint64_t file_size, uint32_t block_size);
+
+/* Results: count, then copies into caller buffers (offsets: count u64; values: 2*count u32,
+ * [2i] = element under the first literal, [2i+1] = element under the first opposite-case letter). */
+uint64_t mmg_results_count(const mmg_results *r);
+int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t *offsets, uint32_t *values);
+/* Device-resident views (valid until mmg_results_free): offsets as u64[count], values packed
+ * as u32[count] = v0 | v1 << 16.  For NCCL gathers without a host round trip. */
+const uint64_t *mmg_results_device_offsets(const mmg_results *r);
+const uint32_t *mmg_results_device_values(const mmg_results *r);
+void mmg_results_free(mmg_results *r);
+
+/* Timing / accounting of the last scan that produced `r` (for bench.py). */
+typedef struct mmg_scan_stats {
+    float ms_total;          /* device time of the whole scan (CUDA events on the scan's stream), excl. H2D */
+    float ms_filter;         /* the streaming filter kernel (the HBM-bound one) */
+    float ms_h2d;            /* host->device copy, 0 for MMG_MEM_DEVICE */
+    uint32_t launches;       /* kernels launched by this scan */
+    uint32_t fast_path;      /* 1 = tiled streaming path, 0 = generic per-chain path */
+    uint64_t events;         /* candidate windows that needed exact evaluation */
+    uint64_t bytes_scanned;
+} mmg_scan_stats;
+int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
+
+/* Testing knob (returns the previous mode): 0 = automatic; 1 = force the per-chain generic kernels;
+ * 2 = tiled path with exact evaluation of every window (no SWAR filter). */
+int mmg_set_path_override(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMOORE_B200_H */

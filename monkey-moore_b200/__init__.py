@@ -1,0 +1,261 @@
+"""monkey-moore_b200 -- B200-native relative search (Monkey-Moore's hot path) behind the reference's API.
+
+This package is the Python host side of the C-ABI in ``include/mmoore_b200.h`` (implemented by
+``libmmoore_b200.so``, built in-tree from ``csrc/``).  It mirrors the reference's public surface:
+
+* :class:`MonkeyMoore`   <-> ``MonkeyMoore<Ty>``            (/root/reference/include/mmoore/monkey_moore.hpp:18-51)
+* :class:`SearchConfig`  <-> ``mmoore::SearchConfig``       (/root/reference/include/mmoore/search_engine.hpp:23-38)
+* :class:`SearchEngine`  <-> ``mmoore::SearchEngine<T>``    (/root/reference/include/mmoore/search_engine.hpp:47-58)
+
+The directory name contains a hyphen, so import it as ``monkey_moore_b200`` (a shim package at the
+repo root) -- both names resolve to this module.
+
+There is no CPU fallback: importing works anywhere (the library loads without a GPU so that its
+exported symbols can be checked), but every scan raises :class:`MMError` when no CUDA device exists.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmoore_b200.so")
+
+MMG_OK = 0
+ERROR_NAMES = {1: "Skip table index out of bounds", 2: "empty keyword", 3: "pattern never advances",
+               4: "bad argument", 5: "CUDA error", 6: "keyword too long", 7: "out of memory"}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+# every symbol include/mmoore_b200.h declares (tests check the library exports all of them)
+C_ABI_SYMBOLS = [
+    "mmg_last_error", "mmg_device_count", "mmg_program_create_keyword", "mmg_program_create_values",
+    "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
+    "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_num_blocks", "mmg_results_count",
+    "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
+    "mmg_results_stats", "mmg_set_path_override",
+]
+
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_i16p = C.POINTER(C.c_int16)
+
+
+class ScanStats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_filter", C.c_float), ("ms_h2d", C.c_float),
+                ("launches", C.c_uint32), ("fast_path", C.c_uint32), ("events", C.c_uint64),
+                ("bytes_scanned", C.c_uint64)]
+
+
+class MMError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+def build(force=False):
+    """Compiles csrc/ for sm_100a into libmmoore_b200.so (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no fallback implementation)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.mmg_last_error.restype = C.c_char_p
+        l.mmg_device_count.restype = C.c_int
+        l.mmg_program_create_keyword.argtypes = [_u32p, C.c_int, C.c_uint32, _u32p, C.c_int, C.c_int,
+                                                 C.POINTER(C.c_void_p)]
+        l.mmg_program_create_values.argtypes = [_i16p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_program_free.argtypes = [C.c_void_p]
+        l.mmg_program_keyword_len.argtypes = [C.c_void_p]
+        l.mmg_program_mode.argtypes = [C.c_void_p]
+        l.mmg_program_table_size.argtypes = [C.c_void_p]
+        l.mmg_program_table.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _u32p, _u32p]
+        l.mmg_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_engine_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint32,
+                                      C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_num_blocks.restype = C.c_uint64
+        l.mmg_num_blocks.argtypes = [C.c_uint64, C.c_uint32]
+        l.mmg_results_count.restype = C.c_uint64
+        l.mmg_results_count.argtypes = [C.c_void_p]
+        l.mmg_results_copy.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _u64p, _u32p]
+        l.mmg_results_device_offsets.restype = C.c_void_p
+        l.mmg_results_device_offsets.argtypes = [C.c_void_p]
+        l.mmg_results_device_values.restype = C.c_void_p
+        l.mmg_results_device_values.argtypes = [C.c_void_p]
+        l.mmg_results_free.argtypes = [C.c_void_p]
+        l.mmg_results_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
+        l.mmg_set_path_override.argtypes = [C.c_int]
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != MMG_OK:
+        msg = lib().mmg_last_error().decode() or ERROR_NAMES.get(rc, "error %d" % rc)
+        if rc == 1:
+            msg = "Skip table index out of bounds"   # the reference's std::runtime_error text
+        raise MMError(rc, msg)
+
+
+def _codepoints(s):
+    if isinstance(s, str):
+        return [ord(c) for c in s]
+    return [int(c) for c in (s or [])]
+
+
+def _u32(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
+    return a, a.ctypes.data_as(_u32p)
+
+
+def set_path_override(mode):
+    return lib().mmg_set_path_override(int(mode))
+
+
+def device_count():
+    return lib().mmg_device_count()
+
+
+class Results:
+    """Match list of one scan (device resident until freed)."""
+
+    def __init__(self, handle, program):
+        self._h = handle
+        self._program = program
+        self.count = int(lib().mmg_results_count(handle))
+
+    def close(self):
+        if self._h:
+            lib().mmg_results_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __len__(self):
+        return self.count
+
+    def arrays(self):
+        """-> (offsets uint64[n], values uint32[n, 2])"""
+        off = np.zeros(self.count, np.uint64)
+        val = np.zeros((self.count, 2), np.uint32)
+        if self.count:
+            _check(lib().mmg_results_copy(self._h, 0, self.count, off.ctypes.data_as(_u64p),
+                                          val.ctypes.data_as(_u32p)))
+        return off, val
+
+    @property
+    def offsets(self):
+        return self.arrays()[0]
+
+    def device_pointers(self):
+        return lib().mmg_results_device_offsets(self._h), lib().mmg_results_device_values(self._h)
+
+    def stats(self):
+        s = ScanStats()
+        _check(lib().mmg_results_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in ScanStats._fields_}
+
+    def tables(self):
+        """The equivalency_map of every match, as the reference's ``result_type::second``."""
+        _, val = self.arrays()
+        return [self._program.table(int(v[0]), int(v[1])) for v in val]
+
+
+class Program:
+    """A compiled pattern: what one ``MonkeyMoore<Ty>`` instance holds after construction."""
+
+    def __init__(self, bits, keyword=None, wildcard=0, char_seq=(), values=None):
+        self.bits = int(bits)
+        h = C.c_void_p()
+        if values is not None:
+            v = np.ascontiguousarray(np.asarray(values, dtype=np.int16))
+            _check(lib().mmg_program_create_values(v.ctypes.data_as(_i16p), len(v), self.bits, C.byref(h)))
+        else:
+            kw, kwp = _u32(_codepoints(keyword))
+            sq, sqp = _u32(_codepoints(char_seq))
+            _check(lib().mmg_program_create_keyword(kwp, len(kw), int(wildcard), sqp, len(sq), self.bits,
+                                                    C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mmg_program_free(self._h)
+            self._h = None
+
+    @property
+    def keyword_len(self):
+        return lib().mmg_program_keyword_len(self._h)
+
+    @property
+    def mode(self):
+        return lib().mmg_program_mode(self._h)
+
+    def table(self, v0, v1):
+        n = lib().mmg_program_table_size(self._h)
+        k = np.zeros(max(n, 1), np.uint32)
+        v = np.zeros(max(n, 1), np.uint32)
+        lib().mmg_program_table(self._h, int(v0), int(v1), k.ctypes.data_as(_u32p), v.ctypes.data_as(_u32p))
+        return {int(k[i]): int(v[i]) for i in range(n)}
+
+    # -- scans -------------------------------------------------------------------------------
+    def _pointer(self, data):
+        """numpy array (host) or torch CUDA tensor / (ptr, nbytes) tuple (device) -> (ptr, nbytes, mem)"""
+        if isinstance(data, np.ndarray):
+            data = np.ascontiguousarray(data)
+            return data.ctypes.data, data.nbytes, MEM_HOST, data
+        if isinstance(data, tuple):
+            return int(data[0]), int(data[1]), MEM_DEVICE, data
+        # torch tensor
+        t = data.contiguous()
+        nbytes = t.numel() * t.element_size()
+        return t.data_ptr(), nbytes, (MEM_DEVICE if t.is_cuda else MEM_HOST), t
+
+    def search(self, data):
+        """``MonkeyMoore<Ty>::search(data, data_len)``: one chain over the element buffer."""
+        ptr, nbytes, mem, keep = self._pointer(data)
+        h = C.c_void_p()
+        _check(lib().mmg_search(self._h, ptr, nbytes // (self.bits // 8), mem, C.byref(h)))
+        return Results(h, self)
+
+    def engine_scan(self, data, block_size, big_endian=False, file_size=None, first_block=0, num_blocks=0):
+        """The chunk engine of ``SearchEngine<T>::run`` over a file image (or one rank's slice of it)."""
+        ptr, nbytes, mem, keep = self._pointer(data)
+        if file_size is None:
+            file_size = nbytes
+        h = C.c_void_p()
+        _check(lib().mmg_engine_scan(self._h, ptr, nbytes, mem, int(file_size), int(block_size), int(first_block),
+                                     int(num_blocks), int(bool(big_endian)), C.byref(h)))
+        return Results(h, self)
+
+
+class MonkeyMoore:
+    """Mirror of ``MonkeyMoore<Ty>`` (include/mmoore/monkey_moore.hpp:18-51 of the reference).
+
+    ``MonkeyMoore(bits, keyword, wildcard=0, char_seq=())`` or ``MonkeyMoore(bits, values=[...])``.
+    ``search(data)`` returns ``[(position, {char: value})]`` exactly like ``std::vector<result_type>``.
+    """
+
+    def __init__(self, bits, keyword=None, wildcard=0, char_seq=(), values=None):
+        self.program = Program(bits, keyword=keyword, wildcard=wildcard, char_seq=char_seq, values=values)
+
+    def search(self, data):
+        res = self.program.search(data)
+        off, val = res.arrays()
+        out = [(int(o), self.program.table(int(v[0]), int(v[1]))) for o, v in zip(off, val)]
+        res.close()
+        return out
+
+
+from .engine import SearchConfig, SearchEngine, SearchResult, SearchStep  # noqa: E402,F401

@@ -1,0 +1,409 @@
+// capi.cu -- the C-ABI (include/mmoore_b200.h): host orchestration of the scan kernels.
+//
+// Host-side counterparts in the reference (file:line under /root/reference/):
+//   MonkeyMoore<Ty>::search                      src/core/monkey_moore.cpp:41-49
+//   SearchEngine<T>::compute_search_blocks       src/core/search_engine.cpp:218-253
+//   SearchEngine<T>::run worker + merge + sort   src/core/search_engine.cpp:104-172, 193-197
+// There is no CPU implementation of the scan in this library: without a CUDA device every
+// scan entry point returns MMG_ERR_CUDA.
+#include "../../include/mmoore_b200.h"
+#include "launch.h"
+#include "pattern.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            throw ScanError{e_ == cudaErrorMemoryAllocation ? MMG_ERR_NOMEM : MMG_ERR_CUDA};       \
+        }                                                                                          \
+    } while (0)
+
+struct ScanError { int code; };
+
+int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everything tiles (testing)
+
+struct DeviceInfo {
+    int device = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+};
+
+// one stream per host thread and device
+DeviceInfo &device_info() {
+    thread_local std::vector<DeviceInfo> infos;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) throw ScanError{fail(MMG_ERR_CUDA, "no usable CUDA device")};
+    for (auto &d : infos)
+        if (d.device == dev) return d;
+    DeviceInfo d;
+    d.device = dev;
+    CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;   // keep freed scratch in the pool: steady-state scans do not hit cudaMalloc
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    infos.push_back(d);
+    return infos.back();
+}
+
+// stream-ordered scratch that is released when the scan ends
+struct Arena {
+    cudaStream_t stream;
+    std::vector<void *> ptrs;
+    explicit Arena(cudaStream_t s) : stream(s) {}
+    ~Arena() { for (void *p : ptrs) cudaFreeAsync(p, stream); }
+    template <class T> T *get(size_t n) {
+        void *p = nullptr;
+        CU(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), stream));
+        ptrs.push_back(p);
+        return static_cast<T *>(p);
+    }
+};
+
+}  // namespace
+
+struct mmg_results {
+    uint64_t count = 0;
+    uint64_t *d_off = nullptr;
+    uint32_t *d_val = nullptr;
+    cudaStream_t stream = nullptr;
+    mmg_scan_stats stats{};
+};
+
+namespace {
+
+struct ScanRequest {
+    const mmg_program *prog;
+    const uint8_t *d_bytes;   // device
+    uint64_t S;               // valid bytes
+    uint64_t B;               // block size
+    uint64_t nblocks;
+    uint32_t npads;
+    bool big_endian;
+    uint64_t base_offset;
+    uint32_t report_shift;
+};
+
+void run_generic(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results *res, uint32_t &launches) {
+    const MmgProgram &P = rq.prog->dev;
+    MmgGeom G{};
+    G.data = rq.d_bytes; G.S = rq.S; G.B = rq.B; G.base_offset = rq.base_offset;
+    G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * P.W; G.npads = rq.npads;
+    G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
+    const uint64_t chains = rq.nblocks * rq.npads;
+    if (chains > 0x7FFFFFFFull) throw ScanError{fail(MMG_ERR_ARG, "too many blocks for the generic path")};
+    const uint32_t n = (uint32_t)chains;
+    uint32_t *counts = arena.get<uint32_t>(n);
+    uint64_t *bases = arena.get<uint64_t>(n);
+    uint64_t *bsum = arena.get<uint64_t>((n + 1023) / 1024 + 1);
+    uint64_t *total_d = arena.get<uint64_t>(1);
+    CU(mmg_launch_generic_walk(P, G, counts, nullptr, nullptr, nullptr, dev.stream));
+    CU(mmg_launch_scan(counts, n, bsum, bases, total_d, dev.stream));
+    launches += 4;
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, total_d, sizeof(total), cudaMemcpyDeviceToHost, dev.stream));
+    CU(cudaStreamSynchronize(dev.stream));
+    res->count = total;
+    if (total == 0) return;
+    CU(cudaMallocAsync((void **)&res->d_off, total * sizeof(uint64_t), dev.stream));
+    CU(cudaMallocAsync((void **)&res->d_val, total * sizeof(uint32_t), dev.stream));
+    if (rq.npads == 1) {
+        CU(mmg_launch_generic_walk(P, G, counts, bases, res->d_off, res->d_val, dev.stream));
+        launches += 1;
+    } else {
+        uint64_t *tmp_off = arena.get<uint64_t>(total);
+        uint32_t *tmp_val = arena.get<uint32_t>(total);
+        CU(mmg_launch_generic_walk(P, G, counts, bases, tmp_off, tmp_val, dev.stream));
+        CU(mmg_launch_generic_merge(G.nblocks, counts, bases, tmp_off, tmp_val, res->d_off, res->d_val, dev.stream));
+        launches += 2;
+    }
+}
+
+void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results *res, uint32_t &launches,
+               cudaEvent_t ev_filter_done) {
+    const MmgProgram &P = rq.prog->dev;
+    const int W = P.W;
+    int lag_bytes = (P.ncheck > 0 && P.nkeys >= 0) ? P.chk[0].lag * W : 0;
+    if (!mmg_filter_supported(W, lag_bytes) || g_path_override == 2) lag_bytes = 0;   // evaluate every window exactly
+
+    MmgGeom G{};
+    G.data = rq.d_bytes; G.S = rq.S; G.base_offset = rq.base_offset;
+    G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * W; G.npads = rq.npads;
+    G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
+    if (rq.nblocks == 1) G.B = ((std::max<uint64_t>(std::max(rq.S, rq.B), 1) + MMG_SUBTILE - 1) / MMG_SUBTILE) * MMG_SUBTILE;
+    else G.B = rq.B;
+    const uint64_t spb = G.B / MMG_SUBTILE;
+    const uint64_t last_off = (rq.nblocks - 1) * G.B;
+    const uint64_t nsub64 = (rq.nblocks - 1) * spb + (rq.S - last_off + MMG_SUBTILE - 1) / MMG_SUBTILE;
+    if (spb > 0xFFFFFFFFull || nsub64 > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_ARG, "input too large for one scan")};
+    G.spb = (uint32_t)spb;
+    G.nsub = (uint32_t)nsub64;
+
+    int occ = 1;
+    CU(mmg_filter_occupancy(W, lag_bytes, rq.big_endian, &occ));
+    const int grid = dev.sms * std::max(occ, 1);
+    const uint64_t total_warps = (uint64_t)grid * 8;
+    uint32_t cs = 16;
+    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 4 * total_warps)) cs >>= 1;
+    G.chunk_subs = cs;
+    G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
+
+    MmgScratch X{};
+    const uint32_t npads = rq.npads;
+    X.jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+    X.sub_start = arena.get<uint32_t>(G.nsub);
+    X.sub_count = arena.get<uint32_t>(G.nsub);
+    X.hasmap = arena.get<uint8_t>((size_t)G.nsub * npads);
+    X.maps = arena.get<uint8_t>((size_t)G.nsub * npads * X.jp);
+    X.phase_in = arena.get<uint8_t>((size_t)G.nsub * npads);
+    X.mcount = arena.get<uint32_t>(G.nsub);
+    X.mbase = arena.get<uint64_t>(G.nsub);
+    X.status = arena.get<uint64_t>(4);
+    uint64_t *bsum = arena.get<uint64_t>((G.nsub + 1023) / 1024 + 1);
+
+    // event capacity: private, equally sized regions per filter warp; grown and re-run on overflow
+    uint64_t per_warp = std::max<uint64_t>(256, rq.S / 8 / total_warps);
+    if (lag_bytes == 0) per_warp = std::max<uint64_t>(per_warp, (rq.S / total_warps + MMG_SUBTILE) * 2);
+    uint64_t status[4] = {0, 0, 0, 0};
+    for (int attempt = 0;; attempt++) {
+        if (per_warp * total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
+        X.ev_per_warp = (uint32_t)per_warp;
+        X.ev = arena.get<uint32_t>(per_warp * total_warps);
+        CU(cudaMemsetAsync(X.status, 0, 4 * sizeof(uint64_t), dev.stream));
+        CU(mmg_launch_filter(P, G, X, lag_bytes, grid, dev.stream));
+        if (attempt == 0) CU(cudaEventRecord(ev_filter_done, dev.stream));
+        CU(mmg_launch_maps(P, G, X, dev.stream));
+        CU(mmg_launch_phases(P, G, X, dev.stream));
+        CU(mmg_launch_walk(P, G, X, dev.stream));
+        CU(mmg_launch_scan(X.mcount, G.nsub, bsum, X.mbase, &X.status[2], dev.stream));
+        launches += 7;
+        CU(cudaMemcpyAsync(status, X.status, sizeof(status), cudaMemcpyDeviceToHost, dev.stream));
+        CU(cudaStreamSynchronize(dev.stream));
+        if (status[0] <= per_warp) break;
+        if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
+        per_warp = status[0] + status[0] / 4 + 64;
+    }
+    res->stats.events = status[1];
+    res->count = status[2];
+    if (res->count == 0) return;
+    CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), dev.stream));
+    CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), dev.stream));
+    CU(mmg_launch_emit(P, G, X, res->d_off, res->d_val, dev.stream));
+    launches += 1;
+}
+
+int run_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
+             uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, mmg_results **out) {
+    *out = nullptr;
+    mmg_results *res = new mmg_results();
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw ScanError{fail(MMG_ERR_CUDA, "no CUDA device: this library has no CPU fallback")};
+        DeviceInfo &dev = device_info();
+        res->stream = dev.stream;
+        res->stats.bytes_scanned = nbytes;
+        if (nbytes == 0 || nblocks == 0) { *out = res; return MMG_OK; }
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventCreate(&e3));
+        uint32_t launches = 0;
+        {
+            Arena arena(dev.stream);
+            const uint8_t *d_bytes = static_cast<const uint8_t *>(bytes);
+            CU(cudaEventRecord(e0, dev.stream));
+            if (mem == MMG_MEM_HOST) {
+                uint8_t *buf = arena.get<uint8_t>(nbytes + 16);
+                CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, dev.stream));
+                d_bytes = buf;
+            } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
+                throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
+            }
+            CU(cudaEventRecord(e1, dev.stream));
+
+            ScanRequest rq{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
+            const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
+            const bool tiled = regular && g_path_override != 1;
+            res->stats.fast_path = tiled;
+            if (tiled) run_tiled(rq, dev, arena, res, launches, e2);
+            else { run_generic(rq, dev, arena, res, launches); CU(cudaEventRecord(e2, dev.stream)); }
+            CU(cudaEventRecord(e3, dev.stream));
+            CU(cudaStreamSynchronize(dev.stream));
+        }
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1)); res->stats.ms_h2d = mem == MMG_MEM_HOST ? ms : 0.f;
+        CU(cudaEventElapsedTime(&ms, e1, e2)); res->stats.ms_filter = ms;
+        CU(cudaEventElapsedTime(&ms, e1, e3)); res->stats.ms_total = ms;
+        res->stats.launches = launches;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+        *out = res;
+        return MMG_OK;
+    } catch (const ScanError &e) {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (e2) cudaEventDestroy(e2);
+        if (e3) cudaEventDestroy(e3);
+        mmg_results_free(res);
+        cudaGetLastError();
+        return e.code;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mmg_last_error(void) { return g_err.c_str(); }
+
+int mmg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// testing knob: 0 auto, 1 force the per-chain generic kernels, 2 force exact evaluation of every window
+int mmg_set_path_override(int mode) {
+    int old = g_path_override;
+    g_path_override = mode;
+    return old;
+}
+
+int mmg_program_create_keyword(const uint32_t *keyword, int keyword_len, uint32_t wildcard, const uint32_t *char_seq,
+                               int char_seq_len, int elem_bits, mmg_program **out) {
+    if (!out) return fail(MMG_ERR_ARG, "out is null");
+    std::string err;
+    int rc = mmg_compile_pattern(keyword, keyword_len, wildcard, char_seq, char_seq_len, false, elem_bits, out, err);
+    if (rc != MMG_OK) g_err = err;
+    return rc;
+}
+
+int mmg_program_create_values(const int16_t *values, int n, int elem_bits, mmg_program **out) {
+    if (!out) return fail(MMG_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n <= 0 || !values) return fail(MMG_ERR_EMPTY, "empty value list");
+    // static_cast<CharType>(short): /root/reference/src/core/monkey_moore.cpp:33-35
+    std::vector<uint32_t> kw(n);
+    for (int i = 0; i < n; i++) kw[i] = static_cast<uint32_t>(static_cast<int32_t>(values[i]));
+    std::string err;
+    int rc = mmg_compile_pattern(kw.data(), n, 0, nullptr, 0, true, elem_bits, out, err);
+    if (rc != MMG_OK) g_err = err;
+    return rc;
+}
+
+void mmg_program_free(mmg_program *p) { delete p; }
+int mmg_program_keyword_len(const mmg_program *p) { return p->dev.L; }
+int mmg_program_mode(const mmg_program *p) { return p->mode; }
+
+int mmg_program_table_size(const mmg_program *p) {
+    if (p->mode == 2) return 0;
+    if (p->char_seq.empty()) return 2;
+    return static_cast<int>(p->seq_index.size());
+}
+
+void mmg_program_table(const mmg_program *p, uint32_t v0, uint32_t v1, uint32_t *keys, uint32_t *values) {
+    const uint32_t mask = p->elem_bits == 8 ? 0xFFu : 0xFFFFu;
+    if (p->mode == 2) return;
+    if (p->char_seq.empty()) {
+        // /root/reference/src/core/monkey_moore.cpp:380-385 (simple), :476-512 (wildcard / mixed case)
+        const uint32_t ref = p->mode == 1 ? p->normalized[p->dev.first_lit] : p->keyword[0];
+        const uint32_t dist = v0 - ref;
+        uint32_t upper = 'A' + dist, lower = 'a' + dist;
+        if (p->mode == 1 && p->has_case_change && p->dev.opp_idx >= 0) {
+            const uint32_t odist = v1 - p->keyword[p->dev.opp_idx];
+            if (p->mostly_lowercase) upper = 'A' + odist; else lower = 'a' + odist;
+        }
+        keys[0] = 'A'; values[0] = upper & mask;
+        keys[1] = 'a'; values[1] = lower & mask;
+        return;
+    }
+    // :387-391, :515-520 -- every character of the sequence, shifted by the first literal's distance
+    const uint32_t refc = p->mode == 1 ? p->keyword[p->dev.first_lit] : p->keyword[0];
+    const uint32_t dist = v0 - static_cast<uint32_t>(p->value_of(refc));
+    int n = 0;
+    for (const auto &kv : p->seq_index) {   // std::map: ascending key order, like the reference's result map
+        keys[n] = kv.first;
+        values[n] = (static_cast<uint32_t>(kv.second) + dist) & mask;
+        n++;
+    }
+}
+
+uint64_t mmg_num_blocks(uint64_t file_size, uint32_t block_size) {
+    if (block_size == 0) return 0;
+    return (file_size + block_size - 1) / block_size;
+}
+
+int mmg_search(const mmg_program *p, const void *data, uint64_t data_len, int mem, mmg_results **out) {
+    if (!p || !out || (!data && data_len)) return fail(MMG_ERR_ARG, "null argument");
+    const uint32_t W = p->dev.W;
+    const uint64_t nbytes = data_len * W;
+    return run_scan(p, data, nbytes, mem, nbytes, nbytes ? 1 : 0, 1, false, 0, W == 2 ? 1 : 0, out);
+}
+
+int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
+                    uint32_t block_size, uint64_t first_block, uint64_t num_blocks, int big_endian,
+                    mmg_results **out) {
+    if (!p || !out || (!bytes && nbytes)) return fail(MMG_ERR_ARG, "null argument");
+    if (block_size == 0) return fail(MMG_ERR_ARG, "block_size must be positive");
+    const uint64_t all_blocks = mmg_num_blocks(file_size, block_size);
+    if (first_block > all_blocks) return fail(MMG_ERR_ARG, "first_block beyond the file");
+    if (num_blocks == 0 || first_block + num_blocks > all_blocks) num_blocks = all_blocks - first_block;
+    const uint32_t W = p->dev.W;
+    const uint64_t ov = (uint64_t)(p->dev.L - 1) * W;
+    const uint64_t base = first_block * (uint64_t)block_size;
+    uint64_t need = std::min<uint64_t>(file_size - std::min(base, file_size), num_blocks * (uint64_t)block_size + ov);
+    if (nbytes < need) return fail(MMG_ERR_ARG, "slice shorter than the blocks it must cover");
+    return run_scan(p, bytes, need, mem, block_size, num_blocks, W, big_endian != 0 && W == 2, base, 0, out);
+}
+
+uint64_t mmg_results_count(const mmg_results *r) { return r ? r->count : 0; }
+
+int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t *offsets, uint32_t *values) {
+    if (!r || first + n > r->count) return fail(MMG_ERR_ARG, "range outside the result list");
+    if (n == 0) return MMG_OK;
+    if (offsets) {
+        if (cudaMemcpy(offsets, r->d_off + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(MMG_ERR_CUDA, "copying offsets failed");
+    }
+    if (values) {
+        std::vector<uint32_t> packed(n);
+        if (cudaMemcpy(packed.data(), r->d_val + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(MMG_ERR_CUDA, "copying values failed");
+        for (uint64_t i = 0; i < n; i++) { values[2 * i] = packed[i] & 0xFFFFu; values[2 * i + 1] = packed[i] >> 16; }
+    }
+    return MMG_OK;
+}
+
+const uint64_t *mmg_results_device_offsets(const mmg_results *r) { return r ? r->d_off : nullptr; }
+const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? r->d_val : nullptr; }
+
+void mmg_results_free(mmg_results *r) {
+    if (!r) return;
+    if (r->d_off) cudaFreeAsync(r->d_off, r->stream);
+    if (r->d_val) cudaFreeAsync(r->d_val, r->stream);
+    delete r;
+}
+
+int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out) {
+    if (!r || !out) return fail(MMG_ERR_ARG, "null argument");
+    *out = r->stats;
+    return MMG_OK;
+}
+
+}  // extern "C"

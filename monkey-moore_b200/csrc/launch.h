@@ -1,0 +1,24 @@
+// launch.h -- host-callable launch helpers implemented in scan_kernels.cu
+#ifndef MMG_LAUNCH_H
+#define MMG_LAUNCH_H
+
+#include "scan_kernels.cuh"
+
+bool mmg_filter_supported(int W, int lag_bytes);
+cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_sm);
+cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
+                              cudaStream_t stream);
+cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
+cudaError_t mmg_launch_phases(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
+cudaError_t mmg_launch_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
+cudaError_t mmg_launch_scan(const uint32_t *counts, uint32_t n, uint64_t *bsum, uint64_t *bases, uint64_t *total,
+                            cudaStream_t stream);
+cudaError_t mmg_launch_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                            uint32_t *out_val, cudaStream_t stream);
+cudaError_t mmg_launch_generic_walk(const MmgProgram &P, const MmgGeom &G, uint32_t *counts, const uint64_t *bases,
+                                    uint64_t *out_off, uint32_t *out_val, cudaStream_t stream);
+cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases,
+                                     const uint64_t *in_off, const uint32_t *in_val, uint64_t *out_off,
+                                     uint32_t *out_val, cudaStream_t stream);
+
+#endif

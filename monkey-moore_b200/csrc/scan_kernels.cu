@@ -1,0 +1,649 @@
+// scan_kernels.cu -- sm_100a kernels of the relative-search path (see scan_kernels.cuh for the plan).
+//
+// Reference semantics reproduced here (file:line under /root/reference/):
+//   window comparison + advance, simple / value scan   src/core/monkey_moore.cpp:347-405
+//   window comparison + advance, wildcard              src/core/monkey_moore.cpp:449-541
+//   per-block / per-alignment element views            src/core/search_engine.cpp:129-159
+//   endianness normalisation (a byte permute on load)  include/mmoore/byteswap.hpp:70-79
+#include "scan_kernels.cuh"
+
+#define FULL 0xFFFFFFFFu
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// exact window evaluation (the slow path; also the whole of the generic path)
+// ------------------------------------------------------------------------------------------
+
+template <int W, bool BE>
+__device__ __forceinline__ uint32_t ld_elem(const uint8_t *p) {
+    if (W == 1) return p[0];
+    uint32_t a = p[0], b = p[1];
+    return BE ? ((a << 8) | b) : ((b << 8) | a);
+}
+
+// F(s): returns the advance in bits [7:0] and 0x100 when the window matches.
+template <int W, bool BE>
+__device__ __noinline__ uint32_t eval_window(const MmgProgram &P, const uint8_t *w) {
+    const uint32_t vmask = W == 1 ? 0xFFu : 0xFFFFu;
+    for (int c = 0; c < P.ncheck; c++) {
+        const int i = P.chk[c].i;
+        const int cur = (int)ld_elem<W, BE>(w + i * W);
+        const int prv = (int)ld_elem<W, BE>(w + (i - P.chk[c].lag) * W);
+        const int d = cur - prv;
+        const int ed = P.chk[c].ed;
+        const bool pass = P.modular ? ((((uint32_t)(d - ed)) & vmask) == 0) : (d == ed);
+        if (!pass) {
+            int sk = P.tab_default;
+            for (int j = 0; j < P.ntab; j++)
+                if (P.tab_key[j] == d) sk = P.tab_val[j];
+            return (uint32_t)min(P.chk[c].cap, sk);
+        }
+    }
+    return 0x100u | (uint32_t)P.match_jump;
+}
+
+// number of elements of the (block, pad) view and whether window start `rel` (bytes from the
+// block start) begins a complete window   (src/core/search_engine.cpp:136-141)
+__device__ __forceinline__ bool window_in_block(const MmgProgram &P, uint32_t npads, uint64_t blk_size, uint64_t rel) {
+    const uint32_t W = P.W;
+    const uint32_t pad = (uint32_t)(rel % W);
+    if (pad >= npads) return false;
+    uint64_t count = blk_size / W;
+    if (pad + count * W > blk_size) count -= 1;
+    return rel / W + (uint64_t)P.L <= count;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: streaming filter
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint4 load_row(const MmgGeom &G, uint64_t row, int lane) {
+    const uint64_t o = row * MMG_ROW + (uint32_t)lane * 16u;
+    if (o + 16 <= G.S) return ld16(G.data + o);
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 16; b++)
+        if (o + b < G.S) w[b >> 2] |= (uint32_t)G.data[o + b] << (8 * (b & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 32-bit word starting at byte offset OFF of the 32-byte window x[0..7] (x[0..3]: the 16 bytes
+// before this lane's, x[4..7]: this lane's).  BE swaps the bytes of each 16-bit half.
+template <int OFF, bool BE>
+__device__ __forceinline__ uint32_t extract(const uint32_t (&x)[8]) {
+    constexpr int q = OFF >> 2, r = OFF & 3;
+    if (!BE) {
+        if (r == 0) return x[q];
+        return __funnelshift_r(x[q], x[q + 1], 8 * r);
+    }
+    constexpr uint32_t sel = (uint32_t)(r + 1) | ((uint32_t)r << 4) | ((uint32_t)(r + 3) << 8) | ((uint32_t)(r + 2) << 12);
+    return __byte_perm(x[q], r == 0 ? 0u : x[q + 1], sel);
+}
+
+// Per-lane candidate detection.  Returns true when any of this lane's 16 positions is flagged;
+// f[] receives what slow_row() needs to name the positions.
+//   W=1: f[k]    bit 8j+7 set  <=> byte position 4k+j flagged (current element at that byte)
+//   W=2: f[c*4+k] has a zero 16-bit half h  <=> the element starting at byte 4k-c+2h is flagged
+template <int W, int LB, bool BE>
+__device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t (&x)[8], uint32_t (&f)[8]) {
+    if (LB == 0) return true;   // evaluate-everything mode
+    const int nk = P.nkeys;
+    if (W == 1) {
+        uint32_t d[4];
+        d[0] = __vsub4(x[4], extract<16 - LB, false>(x));
+        d[1] = __vsub4(x[5], extract<20 - LB, false>(x));
+        d[2] = __vsub4(x[6], extract<24 - LB, false>(x));
+        d[3] = __vsub4(x[7], extract<28 - LB, false>(x));
+        f[0] = f[1] = f[2] = f[3] = 0;
+        for (int j = 0; j < nk; j++) {
+            const uint32_t key = P.keys[j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = d[k] ^ key;          // zero byte <=> difference == key
+                f[k] |= (t - 0x01010101u) & ~t;         // bit 7 of a byte set if that byte (or a lower one) is zero
+            }
+        }
+        f[0] &= 0x80808080u; f[1] &= 0x80808080u; f[2] &= 0x80808080u; f[3] &= 0x80808080u;
+        return (f[0] | f[1] | f[2] | f[3]) != 0;
+    } else {
+        // t = cur + ~prev = (cur - prev - 1) per 16-bit half; key constant C = 1 - key;
+        // min-accumulate t + C: a zero half <=> difference == key
+        uint32_t t[8];
+        t[0] = __vadd2(extract<16, BE>(x), ~extract<16 - LB, BE>(x));
+        t[1] = __vadd2(extract<20, BE>(x), ~extract<20 - LB, BE>(x));
+        t[2] = __vadd2(extract<24, BE>(x), ~extract<24 - LB, BE>(x));
+        t[3] = __vadd2(extract<28, BE>(x), ~extract<28 - LB, BE>(x));
+        t[4] = __vadd2(extract<15, BE>(x), ~extract<15 - LB, BE>(x));
+        t[5] = __vadd2(extract<19, BE>(x), ~extract<19 - LB, BE>(x));
+        t[6] = __vadd2(extract<23, BE>(x), ~extract<23 - LB, BE>(x));
+        t[7] = __vadd2(extract<27, BE>(x), ~extract<27 - LB, BE>(x));
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = 0xFFFFFFFFu;
+        for (int j = 0; j < nk; j++) {
+            const uint32_t key = P.keys[j];
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[k] = __viaddmin_u16x2(t[k], key, f[k]);
+        }
+        uint32_t m = __vminu2(__vminu2(__vminu2(f[0], f[1]), __vminu2(f[2], f[3])),
+                              __vminu2(__vminu2(f[4], f[5]), __vminu2(f[6], f[7])));
+        return ((m & 0xFFFFu) == 0) || ((m >> 16) == 0);
+    }
+}
+
+// 16-bit candidate mask in ascending byte order.  Bit b names the element whose first byte is
+//   W=1: 16*lane + b            W=2: 16*lane + b - 1
+template <int W, int LB>
+__device__ __forceinline__ uint32_t candidate_mask(const uint32_t (&f)[8], bool any) {
+    if (LB == 0) return 0xFFFFu;
+    if (!any) return 0;
+    uint32_t cm = 0;
+    if (W == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) cm |= ((((f[k] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t e = f[k], o = f[4 + k];      // even class (c=0), odd class (c=1)
+            cm |= (uint32_t)((o & 0xFFFFu) == 0) << (4 * k + 0);
+            cm |= (uint32_t)((e & 0xFFFFu) == 0) << (4 * k + 1);
+            cm |= (uint32_t)((o >> 16) == 0) << (4 * k + 2);
+            cm |= (uint32_t)((e >> 16) == 0) << (4 * k + 3);
+        }
+    }
+    return cm;
+}
+
+struct WarpState {
+    uint32_t open_t;       // sub-tile whose event list is being filled
+    uint32_t open_start;   // event index where that list starts
+    uint32_t cursor;       // next free event index of this warp's private region (unclamped)
+};
+
+__device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState st, uint32_t t, int lane) {
+    while (st.open_t < t) {
+        if (lane == 0) {
+            X.sub_start[st.open_t] = st.open_start;
+            X.sub_count[st.open_t] = st.cursor - st.open_start;
+        }
+        st.open_start = st.cursor;
+        st.open_t++;
+    }
+    return st;
+}
+
+// Exact evaluation of one row's flagged windows and ordered append of the resulting events.
+template <int W, bool BE>
+__device__ __noinline__ WarpState slow_row(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, WarpState st,
+                                           uint32_t cm, int64_t lane_first, int64_t s_lo, int64_t s_hi,
+                                           uint64_t blk_off, uint64_t blk_size, uint32_t reg_hi, int lane) {
+    // lane_first: window start of candidate bit 0 of this lane
+    uint32_t evw[16];
+    int n = 0;
+    uint32_t tmin = 0xFFFFFFFFu;
+    while (cm) {
+        const int b = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int64_t s = lane_first + b;
+        if (s < s_lo || s >= s_hi) continue;
+        if (!window_in_block(P, G.npads, blk_size, (uint64_t)s - blk_off)) continue;
+        const uint32_t r = eval_window<W, BE>(P, G.data + s);
+        const uint32_t jump = r & 0xFFu;
+        if (!(r & 0x100u) && jump == (uint32_t)P.J0) continue;      // default advance, no match: not an event
+        const uint32_t ts = (uint32_t)((uint64_t)s >> MMG_SUBTILE_SHIFT);
+        tmin = min(tmin, ts);
+        evw[n++] = ((uint32_t)s & (MMG_SUBTILE - 1)) | (jump << 16) | ((r & 0x100u) ? MMG_EV_MATCH : 0u) | ((ts & 1u) << 31);
+    }
+    const uint32_t tlo = __reduce_min_sync(FULL, tmin);
+    if (tlo == 0xFFFFFFFFu) return st;
+    // a row straddles at most one sub-tile boundary
+    for (uint32_t tt = tlo; tt <= tlo + 1; tt++) {
+        int cnt = 0;
+        for (int i = 0; i < n; i++) cnt += ((evw[i] >> 31) == (tt & 1u));
+        if (!__any_sync(FULL, cnt > 0)) continue;
+        st = close_until(X, st, tt, lane);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        uint32_t at = st.cursor + (uint32_t)(incl - cnt);
+        for (int i = 0; i < n; i++) {
+            if ((evw[i] >> 31) != (tt & 1u)) continue;
+            if (at < reg_hi) X.ev[at] = evw[i] & 0x7FFFFFFFu;
+            at++;
+        }
+        st.cursor += (uint32_t)total;
+    }
+    return st;
+}
+
+template <int W, int LB, bool BE>
+__global__ void __launch_bounds__(256, 2)
+k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t reg_lo = warp * X.ev_per_warp, reg_hi = reg_lo + X.ev_per_warp;
+    // window start = first byte of the current element of comparison 0, minus sigma
+    const int64_t sigma = (LB == 0) ? 0 : (int64_t)P.chk[0].i * W;
+    constexpr int BACK = (LB == 0) ? (W == 2 ? 1 : 0) : LB + (W == 2 ? 1 : 0);   // bytes needed before the lane's own
+    constexpr int NPW = (BACK + 3) / 4;
+    static_assert(NPW <= 4, "lag too long for the tiled filter");
+
+    WarpState st;
+    st.cursor = reg_lo;
+
+    for (uint32_t chunk = warp; chunk < G.nchunks; chunk += nwarps) {
+        const uint32_t t0 = chunk * G.chunk_subs;
+        const uint32_t t1 = min(t0 + G.chunk_subs, G.nsub);
+        const uint32_t bi = t0 / G.spb;
+        const uint64_t blk_off = (uint64_t)bi * G.B;
+        const uint64_t blk_size = min(G.B + (uint64_t)G.ov, G.S - blk_off);
+        const int64_t s_lo = (int64_t)t0 << MMG_SUBTILE_SHIFT, s_hi = (int64_t)t1 << MMG_SUBTILE_SHIFT;
+        st.open_t = t0;
+        st.open_start = st.cursor;
+
+        const uint64_t row0 = (uint64_t)s_lo / MMG_ROW;
+        const uint64_t row1 = (uint64_t)s_hi / MMG_ROW;
+        // the row after the chunk still holds current elements of windows that start inside it
+        const uint64_t last_row = (row1 * MMG_ROW < G.S) ? row1 : row1 - 1;
+
+        uint4 own = load_row(G, row0, lane);
+        uint4 prevown = make_uint4(0, 0, 0, 0);
+        if (NPW > 0 && lane == 31 && row0 > 0) prevown = ld16(G.data + row0 * MMG_ROW - 16);
+
+        for (uint64_t row = row0; row <= last_row; row++) {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (row < last_row) nxt = load_row(G, row + 1, lane);
+
+            uint32_t x[8];
+            x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
+            // previous lane's words; lane 0 takes lane 31's words of the previous row
+            {
+                const int src = (lane + 31) & 31;
+                const bool last = lane == 31;
+                x[0] = x[1] = x[2] = x[3] = 0;
+                if (NPW >= 1) x[3] = __shfl_sync(FULL, last ? prevown.w : own.w, src);
+                if (NPW >= 2) x[2] = __shfl_sync(FULL, last ? prevown.z : own.z, src);
+                if (NPW >= 3) x[1] = __shfl_sync(FULL, last ? prevown.y : own.y, src);
+                if (NPW >= 4) x[0] = __shfl_sync(FULL, last ? prevown.x : own.x, src);
+            }
+
+            uint32_t f[8];
+            const bool any = filter_lane<W, LB, BE>(P, x, f);
+            if (__any_sync(FULL, any)) {
+                const uint32_t cm = candidate_mask<W, LB>(f, any);
+                const int64_t lane_first = (int64_t)(row * MMG_ROW) + lane * 16 - (W == 2 ? 1 : 0) - sigma;
+                st = slow_row<W, BE>(P, G, X, st, cm, lane_first, s_lo, s_hi, blk_off, blk_size, reg_hi, lane);
+            }
+            prevown = own;
+            own = nxt;
+        }
+        st = close_until(X, st, t1, lane);
+    }
+    if (lane == 0) {
+        atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
+        atomicAdd((unsigned long long *)&X.status[1], (unsigned long long)(st.cursor - reg_lo));
+    }
+}
+
+// a filter warp ran out of its private event region: the host grows the buffer and re-runs
+__device__ __forceinline__ bool events_overflowed(const MmgScratch &X) { return X.status[0] > X.ev_per_warp; }
+
+// ------------------------------------------------------------------------------------------
+// K1b: per sub-tile phase maps
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint32_t J0) {
+    // first chain position >= n when the chain sits at x and advances by J0; returned relative to n
+    if (x < n) x += ((n - x + J0 - 1) / J0) * J0;
+    return x - n;
+}
+
+__global__ void __launch_bounds__(128)
+k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G.nsub || events_overflowed(X)) return;
+    const uint32_t n = X.sub_count[t];
+    const uint32_t W = P.W, npads = G.npads;
+    if (n == 0) {
+        for (uint32_t c = 0; c < npads; c++) X.hasmap[t * npads + c] = 0;
+        return;
+    }
+    const uint32_t *ev = X.ev + X.sub_start[t];
+    const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
+    uint32_t x[MMG_MAXL];
+    for (uint32_t c = 0; c < npads; c++) {
+        for (uint32_t e = 0; e < Jmax; e++) x[e] = e;
+        bool any = false;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+            if (W == 2 && (off & 1u) != c) continue;
+            const uint32_t q = off / W, j = MMG_EV_JUMP(w);
+            any = true;
+            for (uint32_t e = 0; e < Jmax; e++) {
+                const uint32_t xe = x[e];
+                if (xe <= q && (J0 == 1 || (q - xe) % J0 == 0)) x[e] = q + j;
+            }
+        }
+        X.hasmap[t * npads + c] = any;
+        if (any) {
+            uint8_t *m = X.maps + (size_t)(t * npads + c) * X.jp;
+            for (uint32_t e = 0; e < Jmax; e++) m[e] = (uint8_t)lattice_advance(x[e], NP, J0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: entry phase of every sub-tile with events, one warp per (block, alignment) chain
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128)
+k_phases(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t npads = G.npads;
+    if (chain >= G.nblocks * npads || events_overflowed(X)) return;
+    const uint32_t bi = chain / npads, c = chain % npads;
+    const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
+    const uint32_t J0 = P.J0, NP = MMG_SUBTILE / P.W;
+    uint32_t ph = 0;   // every chain starts at the first element of its view
+    for (uint32_t tb = t_begin; tb < t_end; tb += 32) {
+        const uint32_t t = tb + lane;
+        const uint32_t hm = (t < t_end) ? X.hasmap[t * npads + c] : 0;
+        const uint32_t mask = __ballot_sync(FULL, hm != 0);
+        const uint32_t nvalid = min(32u, t_end - tb);
+        if (mask == 0) { ph = lattice_advance(ph, nvalid * NP, J0); continue; }
+        for (uint32_t l = 0; l < nvalid; l++) {
+            if ((mask >> l) & 1u) {
+                const uint32_t tt = tb + l;
+                if (lane == 0) X.phase_in[tt * npads + c] = (uint8_t)ph;
+                ph = X.maps[(size_t)(tt * npads + c) * X.jp + ph];
+            } else {
+                ph = lattice_advance(ph, NP, J0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: replay the true chain through each sub-tile's events
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128)
+k_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G.nsub) return;
+    if (events_overflowed(X)) { X.mcount[t] = 0; return; }
+    const uint32_t n = X.sub_count[t];
+    if (n == 0) { X.mcount[t] = 0; return; }
+    const uint32_t W = P.W, npads = G.npads, J0 = P.J0;
+    uint32_t *ev = X.ev + X.sub_start[t];
+    uint32_t xc[2];
+    xc[0] = X.hasmap[t * npads] ? X.phase_in[t * npads] : 0;
+    xc[1] = (npads > 1 && X.hasmap[t * npads + 1]) ? X.phase_in[t * npads + 1] : 0;
+    uint32_t cnt = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+        const uint32_t c = (W == 2) ? (off & 1u) : 0u;
+        const uint32_t q = off / W, x = xc[c];
+        if (x <= q && (J0 == 1 || (q - x) % J0 == 0)) {
+            if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
+            xc[c] = q + MMG_EV_JUMP(w);
+        }
+    }
+    X.mcount[t] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: exclusive prefix sum (u32 counts -> u64 bases); 1024 items per CTA
+// ------------------------------------------------------------------------------------------
+
+#define SCAN_ITEMS 1024
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *warp_sums, uint64_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; i++) { if (i < wid) base += warp_sums[i]; tot += warp_sums[i]; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_sums(const uint32_t *in, uint32_t n, uint64_t *bsum) {
+    __shared__ uint64_t ws[8];
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    uint64_t v = 0;
+    for (int i = 0; i < 4; i++) if (base + i < n) v += in[base + i];
+    uint64_t tot;
+    block_exclusive_scan(v, ws, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_scan_top(uint64_t *bsum, uint32_t nb, uint64_t *total_out) {
+    __shared__ uint64_t ws[8];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 256) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = i < nb ? bsum[i] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_exclusive_scan(v, ws, &tot);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(256) k_scan_final(const uint32_t *in, uint32_t n, const uint64_t *bsum, uint64_t *out) {
+    __shared__ uint64_t ws[8];
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    uint32_t a[4];
+    uint64_t v = 0;
+    for (int i = 0; i < 4; i++) { a[i] = base + i < n ? in[base + i] : 0; v += a[i]; }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan(v, ws, &tot) + bsum[blockIdx.x];
+    for (int i = 0; i < 4; i++) { if (base + i < n) out[base + i] = ex; ex += a[i]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: ordered emission
+// ------------------------------------------------------------------------------------------
+
+template <int W, bool BE>
+__global__ void __launch_bounds__(128)
+k_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
+       uint64_t *out_off, uint32_t *out_val) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G.nsub) return;
+    const uint32_t m = X.mcount[t];
+    if (m == 0) return;
+    uint64_t at = X.mbase[t];
+    const uint32_t n = X.sub_count[t];
+    const uint32_t *ev = X.ev + X.sub_start[t];
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t w = ev[i];
+        if (!(w & MMG_EV_VISITED)) continue;
+        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
+        out_off[at] = (G.base_offset + s) >> G.report_shift;
+        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
+        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
+        out_val[at] = v0 | (v1 << 16);
+        at++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// G*: generic path -- one thread walks one (block, alignment) chain, any geometry
+// ------------------------------------------------------------------------------------------
+
+template <int W, bool BE>
+__global__ void __launch_bounds__(128)
+g_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, uint32_t *counts, const uint64_t *bases,
+       uint64_t *out_off, uint32_t *out_val) {
+    const uint64_t chain = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= (uint64_t)G.nblocks * G.npads) return;
+    const uint64_t bi = chain / G.npads, pad = chain % G.npads;
+    const uint64_t off = bi * G.B;
+    const uint64_t size = min(G.B + (uint64_t)G.ov, G.S - off);
+    uint64_t count = size / W;
+    if (pad + count * W > size) count -= 1;
+    const uint8_t *base = G.data + off + pad;
+    const uint64_t L = (uint64_t)P.L;
+    uint64_t k = 0;
+    uint32_t n = 0;
+    uint64_t at = bases ? bases[chain] : 0;
+    while (k + L <= count) {
+        const uint32_t r = eval_window<W, BE>(P, base + k * W);
+        if (r & 0x100u) {
+            if (bases) {
+                const uint64_t s = off + pad + k * W;
+                out_off[at] = (G.base_offset + s) >> G.report_shift;
+                const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
+                const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
+                out_val[at] = v0 | (v1 << 16);
+                at++;
+            }
+            n++;
+        }
+        k += r & 0xFFu;
+    }
+    if (!bases) counts[chain] = n;
+}
+
+// two alignments of one block interleave by offset: merge them (offsets are unique)
+__global__ void __launch_bounds__(128)
+g_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases, const uint64_t *in_off, const uint32_t *in_val,
+        uint64_t *out_off, uint32_t *out_val) {
+    const uint64_t chain = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= (uint64_t)nblocks * 2) return;
+    const uint64_t sib = chain ^ 1;
+    const uint64_t blockbase = bases[chain & ~1ull];
+    const uint64_t *mine = in_off + bases[chain], *other = in_off + bases[sib];
+    const uint32_t nm = counts[chain], no = counts[sib];
+    for (uint32_t a = 0; a < nm; a++) {
+        const uint64_t v = mine[a];
+        uint32_t lo = 0, hi = no;   // elements of the sibling list smaller than v
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (other[mid] < v) lo = mid + 1; else hi = mid; }
+        out_off[blockbase + a + lo] = v;
+        out_val[blockbase + a + lo] = in_val[bases[chain] + a];
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launch helpers (called from capi.cu)
+// ------------------------------------------------------------------------------------------
+
+#include "launch.h"
+
+#define FILTER_CASE(W_, LB_)                                                                             \
+    case LB_:                                                                                            \
+        if (be) { fn = (const void *)k_filter<W_, LB_, true>; } else { fn = (const void *)k_filter<W_, LB_, false>; } \
+        break;
+
+// Picks the filter instantiation for (W, lag bytes, endianness); nullptr when the lag is not tiled.
+static const void *filter_kernel(int W, int lag_bytes, bool be) {
+    const void *fn = nullptr;
+    if (W == 1) {
+        be = false;
+        switch (lag_bytes) {
+            FILTER_CASE(1, 0) FILTER_CASE(1, 1) FILTER_CASE(1, 2) FILTER_CASE(1, 3) FILTER_CASE(1, 4)
+            FILTER_CASE(1, 5) FILTER_CASE(1, 6) FILTER_CASE(1, 7) FILTER_CASE(1, 8)
+            default: break;
+        }
+    } else {
+        switch (lag_bytes) {
+            FILTER_CASE(2, 0) FILTER_CASE(2, 2) FILTER_CASE(2, 4) FILTER_CASE(2, 6) FILTER_CASE(2, 8)
+            default: break;
+        }
+    }
+    return fn;
+}
+
+bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_bytes, false) != nullptr; }
+
+cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_sm) {
+    const void *fn = filter_kernel(W, lag_bytes, be);
+    if (!fn) return cudaErrorInvalidValue;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, 256, 0);
+}
+
+cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
+                              cudaStream_t stream) {
+    const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0);
+    if (!fn) return cudaErrorInvalidValue;
+    void *args[] = {(void *)&P, (void *)&G, (void *)&X};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(256), args, 0, stream);
+}
+
+cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    k_maps<<<(G.nsub + 127) / 128, 128, 0, stream>>>(P, G, X);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_phases(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    const uint64_t chains = (uint64_t)G.nblocks * G.npads;
+    k_phases<<<(unsigned)((chains * 32 + 127) / 128), 128, 0, stream>>>(P, G, X);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    k_walk<<<(G.nsub + 127) / 128, 128, 0, stream>>>(P, G, X);
+    return cudaGetLastError();
+}
+
+// exclusive scan of n u32 counts into u64 bases; bsum must hold ceil(n/1024) entries; *total receives the sum
+cudaError_t mmg_launch_scan(const uint32_t *counts, uint32_t n, uint64_t *bsum, uint64_t *bases, uint64_t *total,
+                            cudaStream_t stream) {
+    if (n == 0) return cudaMemsetAsync(total, 0, sizeof(uint64_t), stream);
+    const uint32_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    k_scan_sums<<<nb, 256, 0, stream>>>(counts, n, bsum);
+    k_scan_top<<<1, 256, 0, stream>>>(bsum, nb, total);
+    k_scan_final<<<nb, 256, 0, stream>>>(counts, n, bsum, bases);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                            uint32_t *out_val, cudaStream_t stream) {
+    const unsigned grid = (G.nsub + 127) / 128;
+    if (P.W == 1) k_emit<1, false><<<grid, 128, 0, stream>>>(P, G, X, out_off, out_val);
+    else if (G.big_endian) k_emit<2, true><<<grid, 128, 0, stream>>>(P, G, X, out_off, out_val);
+    else k_emit<2, false><<<grid, 128, 0, stream>>>(P, G, X, out_off, out_val);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_generic_walk(const MmgProgram &P, const MmgGeom &G, uint32_t *counts, const uint64_t *bases,
+                                    uint64_t *out_off, uint32_t *out_val, cudaStream_t stream) {
+    const uint64_t chains = (uint64_t)G.nblocks * G.npads;
+    const unsigned grid = (unsigned)((chains + 127) / 128);
+    if (P.W == 1) g_walk<1, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    else if (G.big_endian) g_walk<2, true><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    else g_walk<2, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases,
+                                     const uint64_t *in_off, const uint32_t *in_val, uint64_t *out_off,
+                                     uint32_t *out_val, cudaStream_t stream) {
+    const uint64_t chains = (uint64_t)nblocks * 2;
+    g_merge<<<(unsigned)((chains + 127) / 128), 128, 0, stream>>>(nblocks, counts, bases, in_off, in_val, out_off, out_val);
+    return cudaGetLastError();
+}

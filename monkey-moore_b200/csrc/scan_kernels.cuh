@@ -1,0 +1,69 @@
+// scan_kernels.cuh -- device-side data model of the B200 relative-search path.
+//
+// The reference walks each (block, alignment) buffer with a sequential, lossy Boyer-Moore
+// chain  s <- s + jump(s)  (/root/reference/src/core/monkey_moore.cpp:347-405, 449-541) and
+// restarts it at every engine block (/root/reference/src/core/search_engine.cpp:129-159).
+// Bit-exact results therefore need that chain replayed.  The GPU formulation:
+//
+//   K1  filter      streams the bytes once (16-byte loads), computes the element-difference
+//                   stream SWAR-style and flags the few windows whose first comparison does
+//                   not end in the default advance J0.  Flagged windows are evaluated exactly
+//                   and become EVENTS (window start, advance, match bit), grouped per sub-tile.
+//   K1b maps        per sub-tile and alignment class: the map  entry phase -> exit phase  of the
+//                   chain through the sub-tile's events (everything else advances by J0).
+//   K2  phases      composes the maps along each chain (one warp per (block, alignment)).
+//   K3  walk        replays the TRUE chain through each sub-tile's events, marks visited matches.
+//   K4  scan        exclusive prefix sum of the per-sub-tile match counts.
+//   K5  emit        writes file offsets + table base values in ascending offset order.
+//
+// Irregular geometries (block size not a multiple of the sub-tile) use the per-chain kernels G*.
+#ifndef MMG_SCAN_KERNELS_CUH
+#define MMG_SCAN_KERNELS_CUH
+
+#include "program.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MMG_SUBTILE 4096u          // bytes of window starts per sub-tile
+#define MMG_SUBTILE_SHIFT 12
+#define MMG_ROW 512u               // bytes one warp loads per step (32 lanes x 16 B)
+#define MMG_ROWS_PER_SUB (MMG_SUBTILE / MMG_ROW)
+
+// event word: [11:0] window start (byte offset in the sub-tile)  [23:16] advance  [24] match  [25] visited
+#define MMG_EV_OFF(e) ((e) & 0xFFFu)
+#define MMG_EV_JUMP(e) (((e) >> 16) & 0xFFu)
+#define MMG_EV_MATCH 0x01000000u
+#define MMG_EV_VISITED 0x02000000u
+
+struct MmgGeom {
+    const uint8_t *data;   // device bytes of the slice; data[0] is file offset base_offset
+    uint64_t S;            // valid bytes in the slice
+    uint64_t B;            // block size (bytes).  search(): one block covering everything
+    uint64_t base_offset;  // added to every reported offset (bytes); search() divides by W afterwards
+    uint32_t nblocks;
+    uint32_t ov;           // (L-1)*W overlap bytes
+    uint32_t npads;        // alignments searched per block: W for the engine, 1 for search()
+    uint32_t big_endian;
+    uint32_t report_shift; // 0: report byte offsets; 1: report element indices of a 16-bit search()
+    uint32_t spb;          // sub-tiles per block (fast path)
+    uint32_t nsub;         // total sub-tiles (fast path)
+    uint32_t chunk_subs;   // sub-tiles per warp work unit (divides spb)
+    uint32_t nchunks;
+};
+
+struct MmgScratch {
+    uint32_t *ev;          // event words, one private region per filter warp
+    uint32_t ev_per_warp;
+    uint32_t *sub_start;   // [nsub] first event of the sub-tile
+    uint32_t *sub_count;   // [nsub]
+    uint8_t *hasmap;       // [nsub*npads]
+    uint8_t *maps;         // [nsub*npads*jp]
+    uint8_t *phase_in;     // [nsub*npads]
+    uint32_t *mcount;      // [nsub] visited matches
+    uint64_t *mbase;       // [nsub] exclusive prefix of mcount
+    uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches
+    uint32_t jp;           // bytes per map (Jmax rounded up to 16)
+};
+
+#endif

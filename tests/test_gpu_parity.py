@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle on the same seeded inputs.
+
+Bar: bit-exact -- same match offsets, same order, same inferred tables."""
+import numpy as np
+import pytest
+
+from _cases import (ENGINE8_BLOCKS, ENGINE8_FILE, ENGINE8_OFFSETS, ENGINE16_BLOCKS_BE, ENGINE16_BLOCKS_LE,
+                    ENGINE16_FILE, ENGINE16_OFFSETS, random_data, random_pattern, ref_kats)
+from _oracle import MMError as OracleError
+from _oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def pat_kwargs(p):
+    return dict(keyword=p.get("keyword"), wildcard=p.get("wildcard", 0), char_seq=p.get("char_seq", ()),
+                values=p.get("values"))
+
+
+def check_search(mm, bits, pat, data, override=0):
+    o = Oracle(bits, **pat_kwargs(pat))
+    prog = mm.Program(bits, **pat_kwargs(pat))
+    old = mm.set_path_override(override)
+    try:
+        res = prog.search(data)
+    finally:
+        mm.set_path_override(old)
+    off, val = res.arrays()
+    opos, ovals = o.search(data)
+    assert off.tolist() == opos.tolist(), (pat, bits, len(data), off[:8], opos[:8])
+    assert [prog.table(int(v[0]), int(v[1])) for v in val] == [o.table(int(v[0]), int(v[1])) for v in ovals]
+    return len(off)
+
+
+def check_engine(mm, bits, pat, file_bytes, block, big_endian, override=0):
+    o = Oracle(bits, **pat_kwargs(pat))
+    prog = mm.Program(bits, **pat_kwargs(pat))
+    old = mm.set_path_override(override)
+    try:
+        res = prog.engine_scan(file_bytes, block, big_endian=big_endian)
+    finally:
+        mm.set_path_override(old)
+    off, val = res.arrays()
+    ooff, ovals = o.engine(file_bytes, block, big_endian=big_endian, wrap32=False)
+    assert off.tolist() == ooff.tolist(), (pat, bits, len(file_bytes), block, big_endian, off[:8], ooff[:8])
+    assert [prog.table(int(v[0]), int(v[1])) for v in val] == [o.table(int(v[0]), int(v[1])) for v in ovals]
+    return len(off)
+
+
+@pytest.mark.parametrize("kat", ref_kats(), ids=lambda k: k["name"])
+@pytest.mark.parametrize("override", [0, 1, 2])
+def test_reference_known_answers(gpu, kat, override):
+    """/root/reference/tests/test_monkey_moore.cpp -- offsets and full value tables."""
+    prog = gpu.Program(kat["bits"], **pat_kwargs(kat))
+    old = gpu.set_path_override(override)
+    try:
+        res = prog.search(kat["data"])
+    finally:
+        gpu.set_path_override(old)
+    assert res.offsets.tolist() == kat["pos"]
+    if kat["maps"] is not None:
+        assert res.tables() == kat["maps"]
+
+
+@pytest.mark.parametrize("override", [0, 1, 2])
+def test_reference_engine_known_answers(gpu, override):
+    """/root/reference/tests/test_search_engine.cpp:26-158 -- tiny files, pathological block sizes, BE."""
+    old = gpu.set_path_override(override)
+    try:
+        cases = [(8, ENGINE8_FILE, ENGINE8_OFFSETS, ENGINE8_BLOCKS, False),
+                 (16, ENGINE16_FILE, ENGINE16_OFFSETS, ENGINE16_BLOCKS_LE, False),
+                 (16, ENGINE16_FILE.byteswap(), ENGINE16_OFFSETS, ENGINE16_BLOCKS_BE, True)]
+        for bits, file, offs, blocks, be in cases:
+            fb = np.ascontiguousarray(file).view(np.uint8)
+            prog = gpu.Program(bits, keyword="text", wildcard=ord("*"))
+            for b in blocks:
+                assert prog.engine_scan(fb, b, big_endian=be).offsets.tolist() == offs, (bits, b, be)
+    finally:
+        gpu.set_path_override(old)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_search_fuzz_small(gpu, seed):
+    """Randomised patterns x data styles, every path (tiled, generic, evaluate-everything)."""
+    rng = np.random.default_rng(1000 + seed)
+    hits = 0
+    for _ in range(60):
+        bits = int(rng.choice([8, 16]))
+        pat = random_pattern(rng, bits)
+        try:
+            Oracle(bits, **pat_kwargs(pat))
+        except OracleError:
+            continue
+        n = int(rng.choice([0, 1, 3, 17, 100, 511, 4096, 5000, 20000]))
+        data = random_data(rng, bits, n, pat)
+        for override in (0, 1, 2):
+            hits += check_search(gpu, bits, pat, data, override)
+    assert hits > 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_search_fuzz_large(gpu, seed):
+    """Longer single chains: many sub-tiles, phase maps composed across tiles."""
+    rng = np.random.default_rng(2000 + seed)
+    hits = 0
+    for _ in range(12):
+        bits = int(rng.choice([8, 16]))
+        pat = random_pattern(rng, bits)
+        try:
+            Oracle(bits, **pat_kwargs(pat))
+        except OracleError:
+            continue
+        n = int(rng.choice([70000, 262144, 1000003]))
+        data = random_data(rng, bits, n, pat)
+        hits += check_search(gpu, bits, pat, data)
+    assert hits > 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_engine_fuzz(gpu, seed):
+    """Block decomposition: regular blocks (tiled path), irregular ones (generic path), LE/BE, odd sizes."""
+    rng = np.random.default_rng(3000 + seed)
+    hits = 0
+    for _ in range(40):
+        bits = int(rng.choice([8, 16]))
+        pat = random_pattern(rng, bits)
+        try:
+            Oracle(bits, **pat_kwargs(pat))
+        except OracleError:
+            continue
+        n = int(rng.choice([0, 5, 64, 301, 5000, 40000, 150001]))
+        data = random_data(rng, bits, n, pat)
+        fb = np.ascontiguousarray(data).view(np.uint8)
+        if rng.random() < 0.3 and len(fb) > 0:
+            fb = np.ascontiguousarray(fb[:-1])
+        block = int(rng.choice([1, 3, 8, 23, 47, 100, 512, 4096, 4096, 8192, 16384, 65536, 524288]))
+        be = bool(rng.random() < 0.4)
+        hits += check_engine(gpu, bits, pat, fb, block, be)
+    assert hits > 0
+
+
+def test_sharded_scan_equals_whole(gpu):
+    """Scanning block ranges separately (one per rank) and concatenating == scanning the file once."""
+    rng = np.random.default_rng(7)
+    for bits, pat in [(8, dict(keyword="abc")), (16, dict(keyword="mo*key*s", wildcard=ord("*")))]:
+        data = random_data(rng, bits, 300000, pat)
+        fb = np.ascontiguousarray(data).view(np.uint8)
+        block = 16384
+        prog = gpu.Program(bits, **pat_kwargs(pat))
+        whole = prog.engine_scan(fb, block).offsets
+        nblocks = (len(fb) + block - 1) // block
+        overlap = (prog.keyword_len - 1) * (bits // 8)
+        parts = []
+        for r in range(3):
+            b0, b1 = r * nblocks // 3, (r + 1) * nblocks // 3
+            lo, hi = b0 * block, min(len(fb), b1 * block + overlap)
+            parts.append(prog.engine_scan(np.ascontiguousarray(fb[lo:hi]), block, file_size=len(fb),
+                                          first_block=b0, num_blocks=b1 - b0).offsets)
+        assert np.concatenate(parts).tolist() == whole.tolist()
