@@ -58,21 +58,6 @@ __device__ __forceinline__ bool window_in_block(const MmgProgram &P, uint32_t np
 // K1: streaming filter
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint4 ld16(const uint8_t *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ uint4 load_row(const MmgGeom &G, uint64_t row, int lane) {
-    const uint64_t o = row * MMG_ROW + (uint32_t)lane * 16u;
-    if (o + 16 <= G.S) return ld16(G.data + o);
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (int b = 0; b < 16; b++)
-        if (o + b < G.S) w[b >> 2] |= (uint32_t)G.data[o + b] << (8 * (b & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 // 32-bit word starting at byte offset OFF of the 32-byte window x[0..7] (x[0..3]: the 16 bytes
 // before this lane's, x[4..7]: this lane's).  BE swaps the bytes of each 16-bit half.
 template <int OFF, bool BE>
@@ -177,116 +162,223 @@ __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState 
     return st;
 }
 
-// Exact evaluation of one row's flagged windows and ordered append of the resulting events.
+// per-chunk constants of the exact-evaluation path
+struct ChunkCtx {
+    int64_t s_lo, s_hi;      // window starts owned by this chunk
+    int64_t q_base;          // queue entries are (window start - q_base)
+    uint64_t blk_off, blk_size;
+    uint32_t reg_hi;
+};
+
+// Exact evaluation of up to 32 queued candidate windows (one per lane, ascending window start)
+// and ordered append of the resulting events to the warp's private event region.
 template <int W, bool BE>
-__device__ __noinline__ WarpState slow_row(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, WarpState st,
-                                           uint32_t cm, int64_t lane_first, int64_t s_lo, int64_t s_hi,
-                                           uint64_t blk_off, uint64_t blk_size, uint32_t reg_hi, int lane) {
-    // lane_first: window start of candidate bit 0 of this lane
-    uint32_t evw[16];
-    int n = 0;
-    uint32_t tmin = 0xFFFFFFFFu;
-    while (cm) {
-        const int b = __ffs(cm) - 1;
-        cm &= cm - 1;
-        const int64_t s = lane_first + b;
-        if (s < s_lo || s >= s_hi) continue;
-        if (!window_in_block(P, G.npads, blk_size, (uint64_t)s - blk_off)) continue;
-        const uint32_t r = eval_window<W, BE>(P, G.data + s);
-        const uint32_t jump = r & 0xFFu;
-        if (!(r & 0x100u) && jump == (uint32_t)P.J0) continue;      // default advance, no match: not an event
-        const uint32_t ts = (uint32_t)((uint64_t)s >> MMG_SUBTILE_SHIFT);
-        tmin = min(tmin, ts);
-        evw[n++] = ((uint32_t)s & (MMG_SUBTILE - 1)) | (jump << 16) | ((r & 0x100u) ? MMG_EV_MATCH : 0u) | ((ts & 1u) << 31);
+__device__ __noinline__ WarpState eval_batch(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, WarpState st,
+                                             const ChunkCtx &C, uint32_t entry, bool have, int lane) {
+    bool is_event = false;
+    uint32_t word = 0, ts = 0;
+    if (have) {
+        const int64_t s = C.q_base + (int64_t)entry;
+        if (s >= C.s_lo && s < C.s_hi && window_in_block(P, G.npads, C.blk_size, (uint64_t)s - C.blk_off)) {
+            const uint32_t r = eval_window<W, BE>(P, G.data + s);
+            const uint32_t jump = r & 0xFFu;
+            if ((r & 0x100u) || jump != (uint32_t)P.J0) {     // default advance without a match is not an event
+                is_event = true;
+                ts = (uint32_t)((uint64_t)s >> MMG_SUBTILE_SHIFT);
+                word = ((uint32_t)s & (MMG_SUBTILE - 1)) | (jump << 16) | ((r & 0x100u) ? MMG_EV_MATCH : 0u);
+            }
+        }
     }
-    const uint32_t tlo = __reduce_min_sync(FULL, tmin);
-    if (tlo == 0xFFFFFFFFu) return st;
-    // a row straddles at most one sub-tile boundary
-    for (uint32_t tt = tlo; tt <= tlo + 1; tt++) {
-        int cnt = 0;
-        for (int i = 0; i < n; i++) cnt += ((evw[i] >> 31) == (tt & 1u));
-        if (!__any_sync(FULL, cnt > 0)) continue;
+    uint32_t pending = __ballot_sync(FULL, is_event);
+    const uint32_t lt = (1u << lane) - 1u;
+    while (pending) {                                        // one round per sub-tile present in the batch
+        const uint32_t tt = __shfl_sync(FULL, ts, __ffs(pending) - 1);
+        const uint32_t grp = __ballot_sync(FULL, is_event && ts == tt);
         st = close_until(X, st, tt, lane);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
+        if (is_event && ts == tt) {
+            const uint32_t at = st.cursor + __popc(grp & lt);
+            if (at < C.reg_hi) X.ev[at] = word;
         }
-        const int total = __shfl_sync(FULL, incl, 31);
-        uint32_t at = st.cursor + (uint32_t)(incl - cnt);
-        for (int i = 0; i < n; i++) {
-            if ((evw[i] >> 31) != (tt & 1u)) continue;
-            if (at < reg_hi) X.ev[at] = evw[i] & 0x7FFFFFFFu;
-            at++;
-        }
-        st.cursor += (uint32_t)total;
+        st.cursor += __popc(grp);
+        pending &= ~grp;
     }
     return st;
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: one private ring per warp ------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#define MMG_STAGE_BYTES 2048u                       // 4 rows
+#define MMG_STAGE_STRIDE (MMG_STAGE_BYTES + 16u)    // + 16-byte left halo
+#define MMG_NSTAGES 4
+#define MMG_QUEUE_CAP 576u                          // < 32 carried + <= 512 new candidates per row
+#define MMG_WARP_SMEM (MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u + MMG_NSTAGES * 8u)   // multiple of 16
+#define MMG_FILTER_WARPS 8
+
+// Stage `k` of a chunk holds the bytes [p0 + k*2048 - 16, p0 + (k+1)*2048) of the slice, clipped to
+// the 16-byte-aligned part of the slice; the unaligned tail (< 16 bytes) is patched in by the lanes.
+__device__ __forceinline__ void issue_stage(const MmgGeom &G, uint64_t p_stage, uint32_t dst, uint32_t bar) {
+    const uint64_t aligned_end = G.S & ~(uint64_t)15;
+    uint64_t lo = p_stage >= 16 ? p_stage - 16 : 0;
+    const uint32_t skip = (uint32_t)(lo + 16 - p_stage);          // 16 when there is no left halo (slice start)
+    uint64_t hi = p_stage + MMG_STAGE_BYTES;
+    if (hi > aligned_end) hi = aligned_end;
+    if (hi > lo) {
+        const uint32_t bytes = (uint32_t)(hi - lo);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(dst + skip, G.data + lo, bytes, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
 template <int W, int LB, bool BE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, 2)
 k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t reg_lo = warp * X.ev_per_warp, reg_hi = reg_lo + X.ev_per_warp;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * MMG_FILTER_WARPS + wib;
+    const uint32_t nwarps = gridDim.x * MMG_FILTER_WARPS;
+    const uint32_t reg_lo = warp * X.ev_per_warp;
     // window start = first byte of the current element of comparison 0, minus sigma
     const int64_t sigma = (LB == 0) ? 0 : (int64_t)P.chk[0].i * W;
-    constexpr int BACK = (LB == 0) ? (W == 2 ? 1 : 0) : LB + (W == 2 ? 1 : 0);   // bytes needed before the lane's own
-    constexpr int NPW = (BACK + 3) / 4;
-    static_assert(NPW <= 4, "lag too long for the tiled filter");
+
+    uint8_t *ring = smem_raw + (size_t)wib * MMG_WARP_SMEM;
+    uint32_t *queue = reinterpret_cast<uint32_t *>(ring + MMG_NSTAGES * MMG_STAGE_STRIDE);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint32_t bar_a = smem_u32(queue + MMG_QUEUE_CAP);
+    if (lane == 0) {
+        for (int i = 0; i < MMG_NSTAGES; i++) mbar_init(bar_a + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
 
     WarpState st;
     st.cursor = reg_lo;
+    uint32_t gstage = 0;      // stages consumed so far by this warp (selects slot and mbarrier parity)
 
     for (uint32_t chunk = warp; chunk < G.nchunks; chunk += nwarps) {
         const uint32_t t0 = chunk * G.chunk_subs;
         const uint32_t t1 = min(t0 + G.chunk_subs, G.nsub);
         const uint32_t bi = t0 / G.spb;
-        const uint64_t blk_off = (uint64_t)bi * G.B;
-        const uint64_t blk_size = min(G.B + (uint64_t)G.ov, G.S - blk_off);
-        const int64_t s_lo = (int64_t)t0 << MMG_SUBTILE_SHIFT, s_hi = (int64_t)t1 << MMG_SUBTILE_SHIFT;
+        ChunkCtx C;
+        C.blk_off = (uint64_t)bi * G.B;
+        C.blk_size = min(G.B + (uint64_t)G.ov, G.S - C.blk_off);
+        C.s_lo = (int64_t)t0 << MMG_SUBTILE_SHIFT;
+        C.s_hi = (int64_t)t1 << MMG_SUBTILE_SHIFT;
+        C.reg_hi = reg_lo + X.ev_per_warp;
         st.open_t = t0;
         st.open_start = st.cursor;
 
-        const uint64_t row0 = (uint64_t)s_lo / MMG_ROW;
-        const uint64_t row1 = (uint64_t)s_hi / MMG_ROW;
-        // the row after the chunk still holds current elements of windows that start inside it
-        const uint64_t last_row = (row1 * MMG_ROW < G.S) ? row1 : row1 - 1;
+        // current-element positions p run over [p0, p_end); the window start is p - sigma (- 1 for
+        // the odd 16-bit class), so the chunk needs sigma + 1 extra bytes past its own window starts
+        const uint64_t p0 = (uint64_t)C.s_lo;
+        const uint64_t p_end = min((uint64_t)C.s_hi + (uint64_t)sigma + 1, (G.S + 15) & ~(uint64_t)15);
+        const uint32_t nst = p_end > p0 ? (uint32_t)((p_end - p0 + MMG_STAGE_BYTES - 1) / MMG_STAGE_BYTES) : 0;
+        C.q_base = (int64_t)p0 - sigma - (W == 2 ? 1 : 0);
+        uint32_t qn = 0;
 
-        uint4 own = load_row(G, row0, lane);
-        uint4 prevown = make_uint4(0, 0, 0, 0);
-        if (NPW > 0 && lane == 31 && row0 > 0) prevown = ld16(G.data + row0 * MMG_ROW - 16);
-
-        for (uint64_t row = row0; row <= last_row; row++) {
-            uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (row < last_row) nxt = load_row(G, row + 1, lane);
-
-            uint32_t x[8];
-            x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
-            // previous lane's words; lane 0 takes lane 31's words of the previous row
-            {
-                const int src = (lane + 31) & 31;
-                const bool last = lane == 31;
-                x[0] = x[1] = x[2] = x[3] = 0;
-                if (NPW >= 1) x[3] = __shfl_sync(FULL, last ? prevown.w : own.w, src);
-                if (NPW >= 2) x[2] = __shfl_sync(FULL, last ? prevown.z : own.z, src);
-                if (NPW >= 3) x[1] = __shfl_sync(FULL, last ? prevown.y : own.y, src);
-                if (NPW >= 4) x[0] = __shfl_sync(FULL, last ? prevown.x : own.x, src);
+        if (lane == 0) {
+            for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
+                const uint32_t slot = (gstage + k) % MMG_NSTAGES;
+                issue_stage(G, p0 + (uint64_t)k * MMG_STAGE_BYTES, ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
             }
-
-            uint32_t f[8];
-            const bool any = filter_lane<W, LB, BE>(P, x, f);
-            if (__any_sync(FULL, any)) {
-                const uint32_t cm = candidate_mask<W, LB>(f, any);
-                const int64_t lane_first = (int64_t)(row * MMG_ROW) + lane * 16 - (W == 2 ? 1 : 0) - sigma;
-                st = slow_row<W, BE>(P, G, X, st, cm, lane_first, s_lo, s_hi, blk_off, blk_size, reg_hi, lane);
-            }
-            prevown = own;
-            own = nxt;
         }
+        for (uint32_t k = 0; k < nst; k++, gstage++) {
+            const uint32_t slot = gstage % MMG_NSTAGES;
+            const uint64_t p_stage = p0 + (uint64_t)k * MMG_STAGE_BYTES;
+            mbar_wait(bar_a + 8 * slot, (gstage / MMG_NSTAGES) & 1u);
+            uint8_t *stage = ring + slot * MMG_STAGE_STRIDE;
+            // unaligned tail of the slice: the last (S mod 16) bytes are not covered by the bulk copy
+            {
+                const uint64_t aligned_end = G.S & ~(uint64_t)15;
+                if (aligned_end != G.S && aligned_end >= p_stage && aligned_end < p_stage + MMG_STAGE_BYTES) {
+                    if (aligned_end + lane < G.S && lane < 16)
+                        stage[16 + (aligned_end - p_stage) + lane] = G.data[aligned_end + lane];
+                    __syncwarp();
+                }
+            }
+#pragma unroll 1
+            for (uint32_t r = 0; r < MMG_STAGE_BYTES / MMG_ROW; r++) {
+                const uint64_t p_row = p_stage + r * MMG_ROW;
+                if (p_row >= p_end) break;
+                const uint4 prv = *reinterpret_cast<const uint4 *>(stage + r * MMG_ROW + lane * 16);
+                const uint4 own = *reinterpret_cast<const uint4 *>(stage + 16 + r * MMG_ROW + lane * 16);
+                uint32_t x[8];
+                x[0] = prv.x; x[1] = prv.y; x[2] = prv.z; x[3] = prv.w;
+                x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
+                uint32_t f[8];
+                const bool any = filter_lane<W, LB, BE>(P, x, f);
+                if (__any_sync(FULL, any)) {
+                    // ordered enqueue of this row's candidates
+                    const uint32_t cm = candidate_mask<W, LB>(f, any);
+                    const int cnt = __popc(cm);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const int total = __shfl_sync(FULL, incl, 31);
+                    uint32_t at = qn + (uint32_t)(incl - cnt);
+                    const uint32_t rel = (uint32_t)(p_row - p0) + (uint32_t)lane * 16u;   // candidate bit 0 of this lane
+                    uint32_t m = cm;
+                    while (m) {
+                        queue[at++] = rel + (uint32_t)(__ffs(m) - 1);
+                        m &= m - 1;
+                    }
+                    qn += (uint32_t)total;
+                    __syncwarp();
+                    uint32_t qh = 0;
+                    while (qn - qh >= 32) {
+                        st = eval_batch<W, BE>(P, G, X, st, C, queue[qh + lane], true, lane);
+                        qh += 32;
+                    }
+                    if (qh) {          // move the < 32 left-overs to the front
+                        const uint32_t left = qn - qh;
+                        const uint32_t v = lane < left ? queue[qh + lane] : 0u;
+                        __syncwarp();
+                        if (lane < left) queue[lane] = v;
+                        qn = left;
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && k + MMG_NSTAGES < nst)
+                issue_stage(G, p_stage + (uint64_t)MMG_NSTAGES * MMG_STAGE_BYTES, ring_a + slot * MMG_STAGE_STRIDE,
+                            bar_a + 8 * slot);
+        }
+        if (qn) st = eval_batch<W, BE>(P, G, X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+        __syncwarp();
         st = close_until(X, st, t1, lane);
     }
     if (lane == 0) {
@@ -583,7 +675,10 @@ bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_by
 cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_sm) {
     const void *fn = filter_kernel(W, lag_bytes, be);
     if (!fn) return cudaErrorInvalidValue;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, 256, 0);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MMG_FILTER_WARPS * MMG_WARP_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, MMG_FILTER_WARPS * 32,
+                                                         MMG_FILTER_WARPS * MMG_WARP_SMEM);
 }
 
 cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
@@ -591,7 +686,7 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
     const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0);
     if (!fn) return cudaErrorInvalidValue;
     void *args[] = {(void *)&P, (void *)&G, (void *)&X};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(256), args, 0, stream);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, MMG_FILTER_WARPS * MMG_WARP_SMEM, stream);
 }
 
 cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
