@@ -123,6 +123,17 @@ typedef struct mmg_scan_stats {
 } mmg_scan_stats;
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
 
+/* Stream selection for the calling thread: use_it != 0 makes every later scan of this thread run on
+ * `cuda_stream` (a cudaStream_t; NULL is the legacy default stream), so a caller can bracket scans with
+ * its own CUDA events; use_it == 0 returns to the library's private non-blocking stream. */
+int mmg_set_stream(void *cuda_stream, int use_it);
+
+/* Synthetic ROM generator used by bench.py and the tests (no reference counterpart; SURVEY.md
+ * section 8d): byte i of the stream = byte (i mod 8) of splitmix64(seed ^ (i / 8)), AND byte_mask.
+ * Fills device memory [device_ptr, device_ptr + nbytes) with stream bytes first_byte ...;
+ * nbytes, first_byte and the pointer must be multiples of 8. */
+int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t first_byte, uint32_t byte_mask);
+
 /* Testing knob (returns the previous mode): 0 = automatic; 1 = force the per-chain generic kernels;
  * 2 = tiled path with exact evaluation of every window (no SWAR filter). */
 int mmg_set_path_override(int mode);

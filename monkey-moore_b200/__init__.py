@@ -33,7 +33,7 @@ C_ABI_SYMBOLS = [
     "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
-    "mmg_results_stats", "mmg_set_path_override",
+    "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream",
 ]
 
 _u32p = C.POINTER(C.c_uint32)
@@ -97,6 +97,8 @@ def lib():
         l.mmg_results_free.argtypes = [C.c_void_p]
         l.mmg_results_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
         l.mmg_set_path_override.argtypes = [C.c_int]
+        l.mmg_set_stream.argtypes = [C.c_void_p, C.c_int]
+        l.mmg_synth_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
         _lib = l
     return _lib
 
@@ -124,6 +126,11 @@ def set_path_override(mode):
     return lib().mmg_set_path_override(int(mode))
 
 
+def set_stream(cuda_stream_handle, use_it=True):
+    """Run later scans of this thread on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    return lib().mmg_set_stream(C.c_void_p(cuda_stream_handle or 0), int(bool(use_it)))
+
+
 def device_count():
     return lib().mmg_device_count()
 
@@ -137,8 +144,8 @@ class Results:
         self.count = int(lib().mmg_results_count(handle))
 
     def close(self):
-        if self._h:
-            lib().mmg_results_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mmg_results_free(self._h)
             self._h = None
 
     __del__ = close
@@ -161,6 +168,17 @@ class Results:
 
     def device_pointers(self):
         return lib().mmg_results_device_offsets(self._h), lib().mmg_results_device_values(self._h)
+
+    def torch_offsets(self):
+        """Match offsets as a torch int64 CUDA tensor (a copy that outlives this object); no host round trip."""
+        import torch
+        if self.count == 0:
+            return torch.empty(0, dtype=torch.int64, device="cuda")
+        ptr, _ = self.device_pointers()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (self.count,), "typestr": "<i8", "data": (ptr, True), "version": 2}
+        return torch.as_tensor(_View(), device="cuda").clone()
 
     def stats(self):
         s = ScanStats()
@@ -190,8 +208,8 @@ class Program:
         self._h = h
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().mmg_program_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mmg_program_free(self._h)
             self._h = None
 
     @property
@@ -258,4 +276,5 @@ class MonkeyMoore:
         return out
 
 
+from .synth import synth_bytes, synth_fill_device  # noqa: E402,F401
 from .engine import SearchConfig, SearchEngine, SearchResult, SearchStep  # noqa: E402,F401

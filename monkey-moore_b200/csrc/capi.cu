@@ -38,11 +38,14 @@ int fail(int code, const std::string &msg) {
 struct ScanError { int code; };
 
 int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everything tiles (testing)
+thread_local cudaStream_t g_user_stream = nullptr;   // set by mmg_set_stream: scans run on the caller's stream
+thread_local bool g_use_user_stream = false;
 
 struct DeviceInfo {
     int device = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream scans run on
+    cudaStream_t own_stream = nullptr;   // this library's non-blocking stream
 };
 
 // one stream per host thread and device
@@ -51,11 +54,12 @@ DeviceInfo &device_info() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) throw ScanError{fail(MMG_ERR_CUDA, "no usable CUDA device")};
     for (auto &d : infos)
-        if (d.device == dev) return d;
+        if (d.device == dev) { d.stream = g_use_user_stream ? g_user_stream : d.own_stream; return d; }
     DeviceInfo d;
     d.device = dev;
     CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
+    d.stream = g_use_user_stream ? g_user_stream : d.own_stream;
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = UINT64_MAX;   // keep freed scratch in the pool: steady-state scans do not hit cudaMalloc
@@ -278,6 +282,12 @@ int mmg_device_count(void) {
     return n;
 }
 
+int mmg_set_stream(void *cuda_stream, int use_it) {
+    g_user_stream = static_cast<cudaStream_t>(cuda_stream);
+    g_use_user_stream = use_it != 0;
+    return MMG_OK;
+}
+
 // testing knob: 0 auto, 1 force the per-chain generic kernels, 2 force exact evaluation of every window
 int mmg_set_path_override(int mode) {
     int old = g_path_override;
@@ -398,6 +408,19 @@ void mmg_results_free(mmg_results *r) {
     if (r->d_off) cudaFreeAsync(r->d_off, r->stream);
     if (r->d_val) cudaFreeAsync(r->d_val, r->stream);
     delete r;
+}
+
+int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t first_byte, uint32_t byte_mask) {
+    if ((nbytes & 7u) || (first_byte & 7u) || (reinterpret_cast<uintptr_t>(device_ptr) & 7u))
+        return fail(MMG_ERR_ARG, "mmg_synth_fill works on 8-byte aligned ranges");
+    try {
+        DeviceInfo &dev = device_info();
+        CU(mmg_launch_synth(static_cast<uint64_t *>(device_ptr), nbytes / 8, seed, first_byte / 8, byte_mask, dev.stream));
+        CU(cudaStreamSynchronize(dev.stream));
+    } catch (const ScanError &e) {
+        return e.code;
+    }
+    return MMG_OK;
 }
 
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out) {

@@ -21,4 +21,7 @@ cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, c
                                      const uint64_t *in_off, const uint32_t *in_val, uint64_t *out_off,
                                      uint32_t *out_val, cudaStream_t stream);
 
+cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint64_t first_word, uint32_t byte_mask,
+                             cudaStream_t stream);
+
 #endif

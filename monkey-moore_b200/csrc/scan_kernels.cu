@@ -7,6 +7,8 @@
 //   endianness normalisation (a byte permute on load)  include/mmoore/byteswap.hpp:70-79
 #include "scan_kernels.cuh"
 
+#include <algorithm>
+
 #define FULL 0xFFFFFFFFu
 
 namespace {
@@ -638,7 +640,34 @@ g_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases, const u
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// synthetic ROM generator (bench / tests): byte i = byte (i mod 8) of splitmix64(seed ^ (i / 8)), AND mask
+// (counter based, chunk addressable, reproducible on CPU -- see synth.py)
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint64_t first_word, uint64_t mask8) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+        out[i] = splitmix64(seed ^ (first_word + i)) & mask8;
+}
+
 }  // namespace
+
+cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint64_t first_word, uint32_t byte_mask,
+                             cudaStream_t stream) {
+    if (nwords == 0) return cudaSuccess;
+    const uint64_t mask8 = 0x0101010101010101ull * (uint64_t)(byte_mask & 0xFFu);
+    const unsigned grid = (unsigned)std::min<uint64_t>((nwords + 255) / 256, 148ull * 16);
+    k_synth<<<grid, 256, 0, stream>>>(out, nwords, seed, first_word, mask8);
+    return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------
 // launch helpers (called from capi.cu)
