@@ -177,7 +177,7 @@ class Results:
         ptr, _ = self.device_pointers()
 
         class _View:
-            __cuda_array_interface__ = {"shape": (self.count,), "typestr": "<i8", "data": (ptr, True), "version": 2}
+            __cuda_array_interface__ = {"shape": (self.count,), "typestr": "<i8", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_View(), device="cuda").clone()
 
     def stats(self):

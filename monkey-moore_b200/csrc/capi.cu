@@ -162,7 +162,7 @@ void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results
     G.nsub = (uint32_t)nsub64;
 
     int occ = 1;
-    CU(mmg_filter_occupancy(W, lag_bytes, rq.big_endian, &occ));
+    CU(mmg_filter_occupancy(W, lag_bytes, rq.big_endian, P.nkeys, &occ));
     const int grid = dev.sms * std::max(occ, 1);
     const uint64_t total_warps = (uint64_t)grid * 8;
     uint32_t cs = 16;

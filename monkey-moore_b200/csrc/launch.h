@@ -5,7 +5,7 @@
 #include "scan_kernels.cuh"
 
 bool mmg_filter_supported(int W, int lag_bytes);
-cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_sm);
+cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *blocks_per_sm);
 cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
                               cudaStream_t stream);
 cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);

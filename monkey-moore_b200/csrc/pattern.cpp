@@ -201,8 +201,10 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
         for (int j = 0; j < d.ntab; j++)
             if (std::min(cap0, d.tab_val[j]) != d.J0) add_key(d.tab_key[j]);
         d.nkeys = static_cast<int32_t>(keys.size());
-        for (size_t j = 0; j < keys.size(); j++)
+        for (size_t j = 0; j < keys.size(); j++) {
             d.keys[j] = d.W == 1 ? keys[j] * 0x01010101u : ((1u - keys[j]) & 0xFFFFu) * 0x00010001u;
+            d.pkeys[j] = (((1u - keys[j]) & 0xFFFFu) << 16) | ((0u - keys[j]) & 0xFFFFu);
+        }
     }
 
     *out = guard.release();

@@ -77,23 +77,44 @@ __device__ __forceinline__ uint32_t extract(const uint32_t (&x)[8]) {
 // f[] receives what slow_row() needs to name the positions.
 //   W=1: f[k]    bit 8j+7 set  <=> byte position 4k+j flagged (current element at that byte)
 //   W=2: f[c*4+k] has a zero 16-bit half h  <=> the element starting at byte 4k-c+2h is flagged
-template <int W, int LB, bool BE>
+// NK > 0: number of keys known at compile time (fully unrolled); NK == 0: P.nkeys at run time.
+template <int W, int LB, bool BE, int NK>
 __device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t (&x)[8], uint32_t (&f)[8]) {
     if (LB == 0) return true;   // evaluate-everything mode
-    const int nk = P.nkeys;
+    const int nk = NK > 0 ? NK : P.nkeys;
     if (W == 1) {
         uint32_t d[4];
         d[0] = __vsub4(x[4], extract<16 - LB, false>(x));
         d[1] = __vsub4(x[5], extract<20 - LB, false>(x));
         d[2] = __vsub4(x[6], extract<24 - LB, false>(x));
         d[3] = __vsub4(x[7], extract<28 - LB, false>(x));
-        f[0] = f[1] = f[2] = f[3] = 0;
-        for (int j = 0; j < nk; j++) {
-            const uint32_t key = P.keys[j];
+        {   // first key peeled: no accumulator initialisation
+            const uint32_t key = P.keys[0];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t t = d[k] ^ key;          // zero byte <=> difference == key
-                f[k] |= (t - 0x01010101u) & ~t;         // bit 7 of a byte set if that byte (or a lower one) is zero
+                f[k] = (t - 0x01010101u) & ~t;          // bit 7 of a byte set if that byte (or a lower one) is zero
+            }
+        }
+        if (NK > 0) {
+#pragma unroll
+            for (int j = 1; j < NK; j++) {
+                const uint32_t key = P.keys[j];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t t = d[k] ^ key;
+                    f[k] |= (t - 0x01010101u) & ~t;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 1; j < nk; j++) {
+                const uint32_t key = P.keys[j];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t t = d[k] ^ key;
+                    f[k] |= (t - 0x01010101u) & ~t;
+                }
             }
         }
         f[0] &= 0x80808080u; f[1] &= 0x80808080u; f[2] &= 0x80808080u; f[3] &= 0x80808080u;
@@ -144,6 +165,42 @@ __device__ __forceinline__ uint32_t candidate_mask(const uint32_t (&f)[8], bool 
         }
     }
     return cm;
+}
+
+// Cheap 16-bit pre-test: is ANY of this lane's 16 element positions possibly flagged?  The element
+// differences are formed with one 32-bit subtraction per word (the borrow between the two halves can
+// only turn a hit in the upper half into 1 or 2 instead of 0), then min-accumulated into a single
+// register.  A superset of filter_lane<2,...>: false positives ~2^-15 per position, no false negatives.
+template <int LB, bool BE, int NK>
+__device__ __forceinline__ bool prefilter16(const MmgProgram &P, const uint32_t (&x)[8]) {
+    uint32_t cur[8], prv[8];
+    cur[0] = extract<16, BE>(x); prv[0] = extract<16 - LB, BE>(x);
+    cur[1] = extract<20, BE>(x); prv[1] = extract<20 - LB, BE>(x);
+    cur[2] = extract<24, BE>(x); prv[2] = extract<24 - LB, BE>(x);
+    cur[3] = extract<28, BE>(x); prv[3] = extract<28 - LB, BE>(x);
+    cur[4] = extract<15, BE>(x); prv[4] = extract<15 - LB, BE>(x);
+    cur[5] = extract<19, BE>(x); prv[5] = extract<19 - LB, BE>(x);
+    cur[6] = extract<23, BE>(x); prv[6] = extract<23 - LB, BE>(x);
+    cur[7] = extract<27, BE>(x); prv[7] = extract<27 - LB, BE>(x);
+    uint32_t acc = 0xFFFFFFFFu;
+    if (NK == 1) {
+        const uint32_t c = P.pkeys[0];          // upper half 1 - key, lower half -key
+#pragma unroll
+        for (int k = 0; k < 8; k += 2)
+            acc = __vimin3_u16x2(acc, cur[k] - prv[k] + c, cur[k + 1] - prv[k + 1] + c);
+    } else {
+        uint32_t d[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = cur[k] - prv[k];
+        const int nk = P.nkeys;
+#pragma unroll 1
+        for (int j = 0; j < nk; j++) {
+            const uint32_t c = P.pkeys[j];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc = __viaddmin_u16x2(d[k], c, acc);
+        }
+    }
+    return ((acc & 0xFFFFu) == 0) || ((acc >> 16) <= 2u);
 }
 
 struct WarpState {
@@ -238,9 +295,14 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 
 #define MMG_STAGE_BYTES 2048u                       // 4 rows
 #define MMG_STAGE_STRIDE (MMG_STAGE_BYTES + 16u)    // + 16-byte left halo
-#define MMG_NSTAGES 4
+#ifndef MMG_NSTAGES
+#define MMG_NSTAGES 3
+#endif
+#ifndef MMG_FILTER_MIN_CTAS
+#define MMG_FILTER_MIN_CTAS 3
+#endif
 #define MMG_QUEUE_CAP 576u                          // < 32 carried + <= 512 new candidates per row
-#define MMG_WARP_SMEM (MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u + MMG_NSTAGES * 8u)   // multiple of 16
+#define MMG_WARP_SMEM ((MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u + MMG_NSTAGES * 8u + 15u) & ~15u)
 #define MMG_FILTER_WARPS 8
 
 // Stage `k` of a chunk holds the bytes [p0 + k*2048 - 16, p0 + (k+1)*2048) of the slice, clipped to
@@ -260,8 +322,14 @@ __device__ __forceinline__ void issue_stage(const MmgGeom &G, uint64_t p_stage, 
     }
 }
 
-template <int W, int LB, bool BE>
-__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, 2)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+template <int W, int LB, bool BE, int NK>
+__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER_MIN_CTAS)
 k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -328,20 +396,26 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                     __syncwarp();
                 }
             }
+            const uint32_t rows = (uint32_t)min((uint64_t)(MMG_STAGE_BYTES / MMG_ROW),
+                                                (p_end - p_stage + MMG_ROW - 1) / MMG_ROW);
+            uint32_t sa = ring_a + slot * MMG_STAGE_STRIDE + (uint32_t)lane * 16u;
 #pragma unroll 1
-            for (uint32_t r = 0; r < MMG_STAGE_BYTES / MMG_ROW; r++) {
-                const uint64_t p_row = p_stage + r * MMG_ROW;
-                if (p_row >= p_end) break;
-                const uint4 prv = *reinterpret_cast<const uint4 *>(stage + r * MMG_ROW + lane * 16);
-                const uint4 own = *reinterpret_cast<const uint4 *>(stage + 16 + r * MMG_ROW + lane * 16);
+            for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW) {
+                const uint4 prv = lds128(sa);
+                const uint4 own = lds128(sa + 16);
                 uint32_t x[8];
                 x[0] = prv.x; x[1] = prv.y; x[2] = prv.z; x[3] = prv.w;
                 x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
                 uint32_t f[8];
-                const bool any = filter_lane<W, LB, BE>(P, x, f);
+                bool any;
+                if (LB == 0) any = true;
+                else if (W == 1) any = filter_lane<1, LB, false, NK>(P, x, f);
+                else any = prefilter16<LB, BE, NK>(P, x);
                 if (__any_sync(FULL, any)) {
-                    // ordered enqueue of this row's candidates
+                    // exact per-position flags (16-bit: only now), then ordered enqueue of the candidates
+                    if (LB != 0 && W == 2) any = any && filter_lane<2, LB, BE, 0>(P, x, f);
                     const uint32_t cm = candidate_mask<W, LB>(f, any);
+                    const uint64_t p_row = p_stage + (uint64_t)r * MMG_ROW;
                     const int cnt = __popc(cm);
                     int incl = cnt;
 #pragma unroll
@@ -675,16 +749,31 @@ cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint
 
 #include "launch.h"
 
+// NK (compile-time key count) per width: 8-bit unrolls up to 4 keys, 16-bit fuses the single-key case.
+template <int W, int LB, bool BE>
+static const void *filter_for_keys(int nkeys) {
+    if (LB == 0) return (const void *)k_filter<W, LB, BE, 0>;
+    if (W == 1) {
+        switch (nkeys) {
+            case 1: return (const void *)k_filter<W, LB, BE, 1>;
+            case 2: return (const void *)k_filter<W, LB, BE, 2>;
+            case 3: return (const void *)k_filter<W, LB, BE, 3>;
+            case 4: return (const void *)k_filter<W, LB, BE, 4>;
+            default: return (const void *)k_filter<W, LB, BE, 0>;
+        }
+    }
+    return nkeys == 1 ? (const void *)k_filter<W, LB, BE, 1> : (const void *)k_filter<W, LB, BE, 0>;
+}
+
 #define FILTER_CASE(W_, LB_)                                                                             \
     case LB_:                                                                                            \
-        if (be) { fn = (const void *)k_filter<W_, LB_, true>; } else { fn = (const void *)k_filter<W_, LB_, false>; } \
+        fn = (W_ == 2 && be) ? filter_for_keys<W_, LB_, (W_ == 2)>(nkeys) : filter_for_keys<W_, LB_, false>(nkeys); \
         break;
 
-// Picks the filter instantiation for (W, lag bytes, endianness); nullptr when the lag is not tiled.
-static const void *filter_kernel(int W, int lag_bytes, bool be) {
+// Picks the filter instantiation for (W, lag bytes, endianness, key count); nullptr when the lag is not tiled.
+static const void *filter_kernel(int W, int lag_bytes, bool be, int nkeys) {
     const void *fn = nullptr;
     if (W == 1) {
-        be = false;
         switch (lag_bytes) {
             FILTER_CASE(1, 0) FILTER_CASE(1, 1) FILTER_CASE(1, 2) FILTER_CASE(1, 3) FILTER_CASE(1, 4)
             FILTER_CASE(1, 5) FILTER_CASE(1, 6) FILTER_CASE(1, 7) FILTER_CASE(1, 8)
@@ -699,10 +788,10 @@ static const void *filter_kernel(int W, int lag_bytes, bool be) {
     return fn;
 }
 
-bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_bytes, false) != nullptr; }
+bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_bytes, false, 1) != nullptr; }
 
-cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_sm) {
-    const void *fn = filter_kernel(W, lag_bytes, be);
+cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *blocks_per_sm) {
+    const void *fn = filter_kernel(W, lag_bytes, be, nkeys);
     if (!fn) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MMG_FILTER_WARPS * MMG_WARP_SMEM);
     if (e != cudaSuccess) return e;
@@ -712,7 +801,7 @@ cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int *blocks_per_
 
 cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
                               cudaStream_t stream) {
-    const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0);
+    const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0, P.nkeys);
     if (!fn) return cudaErrorInvalidValue;
     void *args[] = {(void *)&P, (void *)&G, (void *)&X};
     return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, MMG_FILTER_WARPS * MMG_WARP_SMEM, stream);
