@@ -165,8 +165,8 @@ void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results
     CU(mmg_filter_occupancy(W, lag_bytes, rq.big_endian, P.nkeys, &occ));
     const int grid = dev.sms * std::max(occ, 1);
     const uint64_t total_warps = (uint64_t)grid * 8;
-    uint32_t cs = 16;
-    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 4 * total_warps)) cs >>= 1;
+    uint32_t cs = 8;   // sub-tiles per chunk: small enough that dynamic scheduling balances the tail
+    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 8 * total_warps)) cs >>= 1;
     G.chunk_subs = cs;
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
 

@@ -305,18 +305,18 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 #define MMG_WARP_SMEM ((MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u + MMG_NSTAGES * 8u + 15u) & ~15u)
 #define MMG_FILTER_WARPS 8
 
-// Stage `k` of a chunk holds the bytes [p0 + k*2048 - 16, p0 + (k+1)*2048) of the slice, clipped to
-// the 16-byte-aligned part of the slice; the unaligned tail (< 16 bytes) is patched in by the lanes.
-__device__ __forceinline__ void issue_stage(const MmgGeom &G, uint64_t p_stage, uint32_t dst, uint32_t bar) {
-    const uint64_t aligned_end = G.S & ~(uint64_t)15;
-    uint64_t lo = p_stage >= 16 ? p_stage - 16 : 0;
-    const uint32_t skip = (uint32_t)(lo + 16 - p_stage);          // 16 when there is no left halo (slice start)
-    uint64_t hi = p_stage + MMG_STAGE_BYTES;
-    if (hi > aligned_end) hi = aligned_end;
-    if (hi > lo) {
-        const uint32_t bytes = (uint32_t)(hi - lo);
+// Stage `k` of a chunk holds the slice bytes [p0 + k*2048 - 16, p0 + (k+1)*2048), clipped to
+// [0, copy_end) where copy_end is the 16-byte-aligned end of what the chunk needs; an unaligned tail
+// of the slice (< 16 bytes) is patched in by the lanes.  All positions are relative to p0 (32 bit).
+__device__ __forceinline__ void issue_stage(const uint8_t *chunk_base, bool at_slice_start, uint32_t rel_stage,
+                                            uint32_t copy_end_rel, uint32_t dst, uint32_t bar) {
+    uint32_t skip = 0, lo = rel_stage - 16u;          // rel_stage == 0 && at_slice_start: no left halo exists
+    if (rel_stage == 0 && at_slice_start) { skip = 16u; lo = 0; }
+    const uint32_t hi = min(rel_stage + MMG_STAGE_BYTES, copy_end_rel);
+    if ((int32_t)(hi - lo) > 0) {
+        const uint32_t bytes = hi - lo;
         mbar_expect_tx(bar, bytes);
-        tma_load_1d(dst + skip, G.data + lo, bytes, bar);
+        tma_load_1d(dst + skip, chunk_base + (int32_t)lo, bytes, bar);
     } else {
         mbar_arrive(bar);
     }
@@ -353,9 +353,15 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
 
     WarpState st;
     st.cursor = reg_lo;
-    uint32_t gstage = 0;      // stages consumed so far by this warp (selects slot and mbarrier parity)
+    uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
 
-    for (uint32_t chunk = warp; chunk < G.nchunks; chunk += nwarps) {
+    for (;;) {
+        // dynamic chunk scheduling: warps draw chunks from a global counter (balances the tail)
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        if (chunk >= G.nchunks) break;
+
         const uint32_t t0 = chunk * G.chunk_subs;
         const uint32_t t1 = min(t0 + G.chunk_subs, G.nsub);
         const uint32_t bi = t0 / G.spb;
@@ -371,33 +377,37 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         // current-element positions p run over [p0, p_end); the window start is p - sigma (- 1 for
         // the odd 16-bit class), so the chunk needs sigma + 1 extra bytes past its own window starts
         const uint64_t p0 = (uint64_t)C.s_lo;
-        const uint64_t p_end = min((uint64_t)C.s_hi + (uint64_t)sigma + 1, (G.S + 15) & ~(uint64_t)15);
-        const uint32_t nst = p_end > p0 ? (uint32_t)((p_end - p0 + MMG_STAGE_BYTES - 1) / MMG_STAGE_BYTES) : 0;
+        const uint64_t s16 = (G.S + 15) & ~(uint64_t)15;
+        const uint64_t p_end = min((uint64_t)C.s_hi + (uint64_t)sigma + 1, s16);
+        const uint32_t len = p_end > p0 ? (uint32_t)(p_end - p0) : 0u;         // bytes of p-space to process
+        const uint32_t nst = (len + MMG_STAGE_BYTES - 1) / MMG_STAGE_BYTES;
+        // bulk copies stop at the aligned end of the slice and never go past what the chunk needs
+        const uint64_t aligned_end = G.S & ~(uint64_t)15;
+        const uint64_t want_end = min((p_end + 15) & ~(uint64_t)15, aligned_end);
+        const uint32_t copy_end_rel = want_end > p0 ? (uint32_t)(want_end - p0) : 0u;
+        // unaligned tail of the slice inside this chunk?  (rel position of the first tail byte)
+        const bool has_tail = aligned_end != G.S && aligned_end >= p0 && aligned_end < p0 + len;
+        const uint32_t tail_rel = has_tail ? (uint32_t)(aligned_end - p0) : 0xFFFFFFFFu;
+        const uint8_t *chunk_base = G.data + p0;
+        const bool at_start = p0 == 0;
         C.q_base = (int64_t)p0 - sigma - (W == 2 ? 1 : 0);
         uint32_t qn = 0;
 
         if (lane == 0) {
+            uint32_t sl = slot;
             for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
-                const uint32_t slot = (gstage + k) % MMG_NSTAGES;
-                issue_stage(G, p0 + (uint64_t)k * MMG_STAGE_BYTES, ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
+                issue_stage(chunk_base, at_start, k * MMG_STAGE_BYTES, copy_end_rel, ring_a + sl * MMG_STAGE_STRIDE, bar_a + 8 * sl);
+                sl = sl + 1 == MMG_NSTAGES ? 0 : sl + 1;
             }
         }
-        for (uint32_t k = 0; k < nst; k++, gstage++) {
-            const uint32_t slot = gstage % MMG_NSTAGES;
-            const uint64_t p_stage = p0 + (uint64_t)k * MMG_STAGE_BYTES;
-            mbar_wait(bar_a + 8 * slot, (gstage / MMG_NSTAGES) & 1u);
-            uint8_t *stage = ring + slot * MMG_STAGE_STRIDE;
-            // unaligned tail of the slice: the last (S mod 16) bytes are not covered by the bulk copy
-            {
-                const uint64_t aligned_end = G.S & ~(uint64_t)15;
-                if (aligned_end != G.S && aligned_end >= p_stage && aligned_end < p_stage + MMG_STAGE_BYTES) {
-                    if (aligned_end + lane < G.S && lane < 16)
-                        stage[16 + (aligned_end - p_stage) + lane] = G.data[aligned_end + lane];
-                    __syncwarp();
-                }
+        for (uint32_t k = 0, rel_stage = 0; k < nst; k++, rel_stage += MMG_STAGE_BYTES) {
+            mbar_wait(bar_a + 8 * slot, parity);
+            if (tail_rel - rel_stage < MMG_STAGE_BYTES) {      // patch the last (S mod 16) bytes of the slice
+                if (lane < 16 && aligned_end + lane < G.S)
+                    ring[slot * MMG_STAGE_STRIDE + 16 + (tail_rel - rel_stage) + lane] = G.data[aligned_end + lane];
+                __syncwarp();
             }
-            const uint32_t rows = (uint32_t)min((uint64_t)(MMG_STAGE_BYTES / MMG_ROW),
-                                                (p_end - p_stage + MMG_ROW - 1) / MMG_ROW);
+            const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW, (len - rel_stage + MMG_ROW - 1) / MMG_ROW);
             uint32_t sa = ring_a + slot * MMG_STAGE_STRIDE + (uint32_t)lane * 16u;
 #pragma unroll 1
             for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW) {
@@ -415,7 +425,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                     // exact per-position flags (16-bit: only now), then ordered enqueue of the candidates
                     if (LB != 0 && W == 2) any = any && filter_lane<2, LB, BE, 0>(P, x, f);
                     const uint32_t cm = candidate_mask<W, LB>(f, any);
-                    const uint64_t p_row = p_stage + (uint64_t)r * MMG_ROW;
                     const int cnt = __popc(cm);
                     int incl = cnt;
 #pragma unroll
@@ -425,7 +434,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                     }
                     const int total = __shfl_sync(FULL, incl, 31);
                     uint32_t at = qn + (uint32_t)(incl - cnt);
-                    const uint32_t rel = (uint32_t)(p_row - p0) + (uint32_t)lane * 16u;   // candidate bit 0 of this lane
+                    const uint32_t rel = rel_stage + r * MMG_ROW + (uint32_t)lane * 16u;   // candidate bit 0 of this lane
                     uint32_t m = cm;
                     while (m) {
                         queue[at++] = rel + (uint32_t)(__ffs(m) - 1);
@@ -450,8 +459,9 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
             }
             __syncwarp();
             if (lane == 0 && k + MMG_NSTAGES < nst)
-                issue_stage(G, p_stage + (uint64_t)MMG_NSTAGES * MMG_STAGE_BYTES, ring_a + slot * MMG_STAGE_STRIDE,
-                            bar_a + 8 * slot);
+                issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
+                            ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
+            if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
         }
         if (qn) st = eval_batch<W, BE>(P, G, X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
         __syncwarp();

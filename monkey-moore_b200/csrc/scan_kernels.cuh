@@ -62,7 +62,7 @@ struct MmgScratch {
     uint8_t *phase_in;     // [nsub*npads]
     uint32_t *mcount;      // [nsub] visited matches
     uint64_t *mbase;       // [nsub] exclusive prefix of mcount
-    uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches
+    uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches [3] next chunk (dynamic scheduling)
     uint32_t jp;           // bytes per map (Jmax rounded up to 16)
 };
 
