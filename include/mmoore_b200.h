@@ -123,6 +123,11 @@ typedef struct mmg_scan_stats {
 } mmg_scan_stats;
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
 
+/* Page-locked host staging memory for file -> HBM ingestion (SearchEngine<T>::run reads the file into
+ * such a buffer so that the H2D copy runs at PCIe speed).  NULL when allocation fails / no device. */
+void *mmg_host_alloc(uint64_t nbytes);
+void mmg_host_free(void *p);
+
 /* Stream selection for the calling thread: use_it != 0 makes every later scan of this thread run on
  * `cuda_stream` (a cudaStream_t; NULL is the legacy default stream), so a caller can bracket scans with
  * its own CUDA events; use_it == 0 returns to the library's private non-blocking stream. */

@@ -33,7 +33,7 @@ C_ABI_SYMBOLS = [
     "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
-    "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream",
+    "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
 ]
 
 _u32p = C.POINTER(C.c_uint32)

@@ -173,45 +173,75 @@ void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results
     MmgScratch X{};
     const uint32_t npads = rq.npads;
     X.jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
-    X.sub_start = arena.get<uint32_t>(G.nsub);
-    X.sub_count = arena.get<uint32_t>(G.nsub);
-    X.hasmap = arena.get<uint8_t>((size_t)G.nsub * npads);
-    X.maps = arena.get<uint8_t>((size_t)G.nsub * npads * X.jp);
-    X.phase_in = arena.get<uint8_t>((size_t)G.nsub * npads);
-    X.mcount = arena.get<uint32_t>(G.nsub);
-    X.mbase = arena.get<uint64_t>(G.nsub);
-    X.status = arena.get<uint64_t>(4);
-    uint64_t *bsum = arena.get<uint64_t>((G.nsub + 1023) / 1024 + 1);
+
+    // one allocation for all per-scan scratch; the zero-initialised part comes first
+    const uint32_t ntiles = (G.nsub + 255) / 256;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
+    const size_t o_status = carve(4 * sizeof(uint64_t));
+    const size_t o_ticket = carve(sizeof(uint32_t));
+    const size_t o_lookback = carve((size_t)ntiles * sizeof(uint64_t));
+    const size_t o_chain = carve((size_t)G.nblocks * npads);
+    const size_t zero_bytes = off;
+    const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_hasmap = carve((size_t)G.nsub * npads);
+    const size_t o_maps = carve((size_t)G.nsub * npads * X.jp);
+    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
+    uint8_t *base = arena.get<uint8_t>(off);
+    X.status = reinterpret_cast<uint64_t *>(base + o_status);
+    X.ticket = reinterpret_cast<uint32_t *>(base + o_ticket);
+    X.lookback = reinterpret_cast<uint64_t *>(base + o_lookback);
+    X.chain_has = base + o_chain;
+    X.sub_start = reinterpret_cast<uint32_t *>(base + o_start);
+    X.sub_count = reinterpret_cast<uint32_t *>(base + o_count);
+    X.hasmap = base + o_hasmap;
+    X.maps = base + o_maps;
+    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
+    X.mbase = reinterpret_cast<uint64_t *>(base + o_mbase);
+
+    // optimistic result capacity: what this pattern produced last time plus slack
+    uint64_t cap = std::max<uint64_t>(4096, rq.prog->last_count + rq.prog->last_count / 4 + 1024);
+    CU(cudaMallocAsync((void **)&res->d_off, cap * sizeof(uint64_t), dev.stream));
+    CU(cudaMallocAsync((void **)&res->d_val, cap * sizeof(uint32_t), dev.stream));
 
     // event capacity: private, equally sized regions per filter warp; grown and re-run on overflow
     uint64_t per_warp = std::max<uint64_t>(256, rq.S / 8 / total_warps);
+    if (rq.prog->last_events_per_warp) per_warp = std::max<uint64_t>(256, rq.prog->last_events_per_warp * 2);
     if (lag_bytes == 0) per_warp = std::max<uint64_t>(per_warp, (rq.S / total_warps + MMG_SUBTILE) * 2);
     uint64_t status[4] = {0, 0, 0, 0};
     for (int attempt = 0;; attempt++) {
         if (per_warp * total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
         X.ev_per_warp = (uint32_t)per_warp;
         X.ev = arena.get<uint32_t>(per_warp * total_warps);
-        CU(cudaMemsetAsync(X.status, 0, 4 * sizeof(uint64_t), dev.stream));
+        CU(cudaMemsetAsync(base, 0, zero_bytes, dev.stream));
         CU(mmg_launch_filter(P, G, X, lag_bytes, grid, dev.stream));
         if (attempt == 0) CU(cudaEventRecord(ev_filter_done, dev.stream));
         CU(mmg_launch_maps(P, G, X, dev.stream));
-        CU(mmg_launch_phases(P, G, X, dev.stream));
-        CU(mmg_launch_walk(P, G, X, dev.stream));
-        CU(mmg_launch_scan(X.mcount, G.nsub, bsum, X.mbase, &X.status[2], dev.stream));
-        launches += 7;
+        CU(mmg_launch_phases_walk(P, G, X, dev.stream));
+        CU(mmg_launch_scan_emit(P, G, X, res->d_off, res->d_val, cap, dev.stream));
+        launches += 4;
         CU(cudaMemcpyAsync(status, X.status, sizeof(status), cudaMemcpyDeviceToHost, dev.stream));
         CU(cudaStreamSynchronize(dev.stream));
         if (status[0] <= per_warp) break;
         if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
         per_warp = status[0] + status[0] / 4 + 64;
     }
+    rq.prog->last_events_per_warp = status[0];
+    rq.prog->last_count = status[2];
     res->stats.events = status[1];
     res->count = status[2];
-    if (res->count == 0) return;
-    CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), dev.stream));
-    CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), dev.stream));
-    CU(mmg_launch_emit(P, G, X, res->d_off, res->d_val, dev.stream));
-    launches += 1;
+    if (res->count > cap) {
+        // the optimistic buffer was too small: allocate exactly and emit again from the stored bases
+        CU(cudaFreeAsync(res->d_off, dev.stream));
+        CU(cudaFreeAsync(res->d_val, dev.stream));
+        res->d_off = nullptr; res->d_val = nullptr;
+        CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), dev.stream));
+        CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), dev.stream));
+        CU(mmg_launch_emit(P, G, X, res->d_off, res->d_val, dev.stream));
+        launches += 1;
+    }
 }
 
 int run_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
@@ -408,6 +438,20 @@ void mmg_results_free(mmg_results *r) {
     if (r->d_off) cudaFreeAsync(r->d_off, r->stream);
     if (r->d_val) cudaFreeAsync(r->d_val, r->stream);
     delete r;
+}
+
+void *mmg_host_alloc(uint64_t nbytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(MMG_ERR_NOMEM, "cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void mmg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t first_byte, uint32_t byte_mask) {

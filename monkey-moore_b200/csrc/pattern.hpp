@@ -4,6 +4,7 @@
 
 #include "program.h"
 
+#include <atomic>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -22,6 +23,10 @@ struct mmg_program {
     std::map<uint32_t, int> seq_index;     // char -> position; unknown chars read as 0 (reference: operator[])
     bool has_case_change = false;
     bool mostly_lowercase = false;
+
+    // sizing hints remembered from the previous scan with this pattern (not part of its semantics)
+    mutable std::atomic<uint64_t> last_count{0};
+    mutable std::atomic<uint64_t> last_events_per_warp{0};
 
     int value_of(uint32_t c) const;        // code point, or index in char_seq (0 when absent)
 };

@@ -492,6 +492,7 @@ k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
     if (t >= G.nsub || events_overflowed(X)) return;
     const uint32_t n = X.sub_count[t];
     const uint32_t W = P.W, npads = G.npads;
+    X.mcount[t] = 0;
     if (n == 0) {
         for (uint32_t c = 0; c < npads; c++) X.hasmap[t * npads + c] = 0;
         return;
@@ -514,6 +515,7 @@ k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
         }
         X.hasmap[t * npads + c] = any;
         if (any) {
+            X.chain_has[(t / G.spb) * npads + c] = 1;      // benign race: every writer stores 1
             uint8_t *m = X.maps + (size_t)(t * npads + c) * X.jp;
             for (uint32_t e = 0; e < Jmax; e++) m[e] = (uint8_t)lattice_advance(x[e], NP, J0);
         }
@@ -521,64 +523,55 @@ k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: entry phase of every sub-tile with events, one warp per (block, alignment) chain
+// K2+K3: one warp per (block, alignment) chain composes the sub-tile maps (the entry phase of
+// every sub-tile that has events) and replays the TRUE chain through those sub-tiles' events,
+// marking the matches it visits.  Chains without events exit after one load.
 // ------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(128)
-k_phases(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+k_phases_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
     const int lane = threadIdx.x & 31;
     const uint32_t chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t npads = G.npads;
     if (chain >= G.nblocks * npads || events_overflowed(X)) return;
+    if (!X.chain_has[chain]) return;
     const uint32_t bi = chain / npads, c = chain % npads;
     const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
-    const uint32_t J0 = P.J0, NP = MMG_SUBTILE / P.W;
+    const uint32_t W = P.W, J0 = P.J0, NP = MMG_SUBTILE / W;
     uint32_t ph = 0;   // every chain starts at the first element of its view
     for (uint32_t tb = t_begin; tb < t_end; tb += 32) {
         const uint32_t t = tb + lane;
         const uint32_t hm = (t < t_end) ? X.hasmap[t * npads + c] : 0;
-        const uint32_t mask = __ballot_sync(FULL, hm != 0);
+        uint32_t mask = __ballot_sync(FULL, hm != 0);
         const uint32_t nvalid = min(32u, t_end - tb);
         if (mask == 0) { ph = lattice_advance(ph, nvalid * NP, J0); continue; }
-        for (uint32_t l = 0; l < nvalid; l++) {
-            if ((mask >> l) & 1u) {
-                const uint32_t tt = tb + l;
-                if (lane == 0) X.phase_in[tt * npads + c] = (uint8_t)ph;
-                ph = X.maps[(size_t)(tt * npads + c) * X.jp + ph];
-            } else {
-                ph = lattice_advance(ph, NP, J0);
+        uint32_t my_ph = 0, done = 0;
+        while (mask) {
+            const uint32_t l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);     // event-free sub-tiles in between
+            if ((uint32_t)lane == l) my_ph = ph;
+            ph = X.maps[(size_t)((tb + l) * npads + c) * X.jp + ph];
+            done = l + 1;
+        }
+        if (nvalid > done) ph = lattice_advance(ph, (nvalid - done) * NP, J0);
+        if (hm) {
+            // replay this class's chain through the sub-tile's events
+            const uint32_t n = X.sub_count[t];
+            uint32_t *ev = X.ev + X.sub_start[t];
+            uint32_t x = my_ph, cnt = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                if (W == 2 && (off & 1u) != c) continue;
+                const uint32_t q = off / W;
+                if (x <= q && (J0 == 1 || (q - x) % J0 == 0)) {
+                    if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
+                    x = q + MMG_EV_JUMP(w);
+                }
             }
+            if (cnt) atomicAdd(&X.mcount[t], cnt);
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: replay the true chain through each sub-tile's events
-// ------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(128)
-k_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G.nsub) return;
-    if (events_overflowed(X)) { X.mcount[t] = 0; return; }
-    const uint32_t n = X.sub_count[t];
-    if (n == 0) { X.mcount[t] = 0; return; }
-    const uint32_t W = P.W, npads = G.npads, J0 = P.J0;
-    uint32_t *ev = X.ev + X.sub_start[t];
-    uint32_t xc[2];
-    xc[0] = X.hasmap[t * npads] ? X.phase_in[t * npads] : 0;
-    xc[1] = (npads > 1 && X.hasmap[t * npads + 1]) ? X.phase_in[t * npads + 1] : 0;
-    uint32_t cnt = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t w = ev[i], off = MMG_EV_OFF(w);
-        const uint32_t c = (W == 2) ? (off & 1u) : 0u;
-        const uint32_t q = off / W, x = xc[c];
-        if (x <= q && (J0 == 1 || (q - x) % J0 == 0)) {
-            if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
-            xc[c] = q + MMG_EV_JUMP(w);
-        }
-    }
-    X.mcount[t] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -653,6 +646,69 @@ k_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
     const uint32_t m = X.mcount[t];
     if (m == 0) return;
     uint64_t at = X.mbase[t];
+    const uint32_t n = X.sub_count[t];
+    const uint32_t *ev = X.ev + X.sub_start[t];
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t w = ev[i];
+        if (!(w & MMG_EV_VISITED)) continue;
+        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
+        out_off[at] = (G.base_offset + s) >> G.report_shift;
+        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
+        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
+        out_val[at] = v0 | (v1 << 16);
+        at++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4+K5 fused: single-pass exclusive scan of the per-sub-tile match counts (decoupled look-back,
+// tiles drawn from a ticket counter so that every predecessor is already running) and ordered
+// emission into a buffer of `capacity` entries.  The host re-emits with k_emit when the
+// optimistic capacity was too small.
+// ------------------------------------------------------------------------------------------
+
+#define LB_AGG (1ull << 62)
+#define LB_INCL (2ull << 62)
+#define LB_MASK ((1ull << 62) - 1)
+
+template <int W, bool BE>
+__global__ void __launch_bounds__(256)
+k_scan_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
+            uint64_t *out_off, uint32_t *out_val, uint64_t capacity) {
+    __shared__ uint64_t ws[8];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(X.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t t = tile * 256 + threadIdx.x;
+    const bool bad = events_overflowed(X);
+    const uint32_t m = (t < G.nsub && !bad) ? X.mcount[t] : 0u;
+    uint64_t tot;
+    const uint64_t excl = block_exclusive_scan(m, ws, &tot);
+    if (threadIdx.x == 0) {
+        volatile uint64_t *lb = X.lookback;
+        uint64_t before = 0;
+        if (tile > 0) {
+            lb[tile] = LB_AGG | tot;
+            int64_t j = (int64_t)tile - 1;
+            for (;;) {
+                const uint64_t v = lb[j];
+                if ((v >> 62) == 0) continue;                 // predecessor has not published yet
+                before += v & LB_MASK;
+                if ((v >> 62) == 2) break;
+                j--;
+            }
+        }
+        lb[tile] = LB_INCL | (before + tot);
+        s_prefix = before;
+        if (tile == gridDim.x - 1) X.status[2] = before + tot;
+    }
+    __syncthreads();
+    if (t >= G.nsub) return;
+    uint64_t at = s_prefix + excl;
+    X.mbase[t] = at;
+    if (m == 0 || at + m > capacity) return;
     const uint32_t n = X.sub_count[t];
     const uint32_t *ev = X.ev + X.sub_start[t];
     for (uint32_t i = 0; i < n; i++) {
@@ -822,14 +878,18 @@ cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScra
     return cudaGetLastError();
 }
 
-cudaError_t mmg_launch_phases(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+cudaError_t mmg_launch_phases_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
     const uint64_t chains = (uint64_t)G.nblocks * G.npads;
-    k_phases<<<(unsigned)((chains * 32 + 127) / 128), 128, 0, stream>>>(P, G, X);
+    k_phases_walk<<<(unsigned)((chains * 32 + 127) / 128), 128, 0, stream>>>(P, G, X);
     return cudaGetLastError();
 }
 
-cudaError_t mmg_launch_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
-    k_walk<<<(G.nsub + 127) / 128, 128, 0, stream>>>(P, G, X);
+cudaError_t mmg_launch_scan_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                                 uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    const unsigned grid = (G.nsub + 255) / 256;
+    if (P.W == 1) k_scan_emit<1, false><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
+    else if (G.big_endian) k_scan_emit<2, true><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
+    else k_scan_emit<2, false><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
     return cudaGetLastError();
 }
 

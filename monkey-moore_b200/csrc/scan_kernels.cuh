@@ -11,10 +11,10 @@
 //                   and become EVENTS (window start, advance, match bit), grouped per sub-tile.
 //   K1b maps        per sub-tile and alignment class: the map  entry phase -> exit phase  of the
 //                   chain through the sub-tile's events (everything else advances by J0).
-//   K2  phases      composes the maps along each chain (one warp per (block, alignment)).
-//   K3  walk        replays the TRUE chain through each sub-tile's events, marks visited matches.
-//   K4  scan        exclusive prefix sum of the per-sub-tile match counts.
-//   K5  emit        writes file offsets + table base values in ascending offset order.
+//   K2+K3 phases/walk  one warp per (block, alignment) chain composes the maps and replays the TRUE
+//                   chain through each sub-tile's events, marking the matches it visits.
+//   K4+K5 scan/emit single-pass prefix sum of the per-sub-tile match counts fused with the ordered
+//                   emission of file offsets + table base values.
 //
 // Irregular geometries (block size not a multiple of the sub-tile) use the per-chain kernels G*.
 #ifndef MMG_SCAN_KERNELS_CUH
@@ -59,10 +59,12 @@ struct MmgScratch {
     uint32_t *sub_count;   // [nsub]
     uint8_t *hasmap;       // [nsub*npads]
     uint8_t *maps;         // [nsub*npads*jp]
-    uint8_t *phase_in;     // [nsub*npads]
+    uint8_t *chain_has;    // [nblocks*npads] chain has at least one event (zeroed by the host)
     uint32_t *mcount;      // [nsub] visited matches
     uint64_t *mbase;       // [nsub] exclusive prefix of mcount
     uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches [3] next chunk (dynamic scheduling)
+    uint64_t *lookback;    // [ceil(nsub/256)] decoupled look-back words of the match-count scan (zeroed by the host)
+    uint32_t *ticket;      // tile ticket of the scan (zeroed by the host)
     uint32_t jp;           // bytes per map (Jmax rounded up to 16)
 };
 
