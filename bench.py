@@ -159,7 +159,7 @@ def run_ours(args, w):
 
     import monkey_moore_b200 as mm
     import monkey_moore_b200.workloads as wl
-    from monkey_moore_b200.distributed import gather_offsets, shard_bytes
+    from monkey_moore_b200.distributed import PackedGather, shard_bytes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,6 +185,8 @@ def run_ours(args, w):
     mm.set_stream(stream.cuda_stream, True)
     torch.cuda.synchronize()
 
+    gather = PackedGather(dist, torch, rank, world, len(progs)) if world > 1 else None
+
     def step(collect=None):
         launches, filt_ms, filt_bytes = 0, 0.0, 0
         found = []
@@ -196,13 +198,11 @@ def run_ours(args, w):
             filt_ms += st["ms_filter"]
             filt_bytes += st["bytes_scanned"] + 8 * res.count
             if world > 1 or collect is not None:
-                t = res.torch_offsets()
-                if world > 1:
-                    t = gather_offsets(dist, torch, t, rank, world)
-                if collect is not None and t is not None:
-                    found.append(t)
+                found.append(res.torch_offsets())
             res.close()
-        if collect is not None:
+        if world > 1:
+            found = gather(found)           # ONE collective per step: all searches' offsets to rank 0
+        if collect is not None and found is not None:
             collect.extend(found)
         return launches, filt_ms, filt_bytes
 

@@ -45,3 +45,62 @@ def gather_offsets(dist, torch, offsets, rank, world, group=None):
     if offsets.numel():
         dist.send(offsets, dst=0, group=group)
     return None
+
+
+class PackedGather:
+    """One NCCL collective per step instead of (all-gather of counts + send/recv) per search.
+
+    Every rank packs the offset lists of all searches of a step into one fixed-size int64 buffer
+    ``[n_0, ..., n_{k-1}, offsets_0 ..., offsets_{k-1} ...]`` and a single ``gather`` moves the buffers to
+    rank 0.  A rank whose lists do not fit sends the remainder point-to-point; rank 0 learns that from
+    the gathered header, so no extra collective is needed in the common (sparse) case.
+    """
+
+    def __init__(self, dist, torch, rank, world, nlists, capacity=8192, device="cuda", group=None):
+        self.dist, self.torch, self.rank, self.world = dist, torch, rank, world
+        self.nlists, self.cap, self.group = nlists, int(capacity), group
+        self.buf = torch.zeros(self.cap, dtype=torch.int64, device=device)
+        self.recv = [torch.zeros(self.cap, dtype=torch.int64, device=device) for _ in range(world)] if rank == 0 else None
+
+    def __call__(self, lists):
+        """lists: ``nlists`` int64 tensors on this rank.  Rank 0 gets ``nlists`` concatenated tensors (rank
+        order == file order), other ranks get None."""
+        torch, dist = self.torch, self.dist
+        assert len(lists) == self.nlists
+        room = self.cap - self.nlists
+        at, spill = self.nlists, []
+        header = []
+        for t in lists:
+            n = int(t.numel())
+            header.append(n)
+            fit = min(n, max(0, room - (at - self.nlists)))
+            if fit:
+                self.buf[at:at + fit] = t[:fit]
+            at += fit
+            if fit < n:
+                spill.append(t[fit:])
+        self.buf[: self.nlists] = torch.tensor(header, dtype=torch.int64).to(self.buf.device, non_blocking=True)
+        dist.gather(self.buf, self.recv, dst=0, group=self.group)
+        if self.rank != 0:
+            for t in spill:
+                dist.send(t.contiguous(), dst=0, group=self.group)
+            return None
+        heads = torch.stack([r[: self.nlists] for r in self.recv]).cpu().tolist()     # the only host read of a step
+        out = [[] for _ in range(self.nlists)]
+        for r in range(self.world):
+            at, used = self.nlists, 0
+            for k in range(self.nlists):
+                n = heads[r][k]
+                fit = min(n, max(0, room - used))
+                piece = self.recv[r][at:at + fit].clone()
+                at += fit
+                used += fit
+                if fit < n:
+                    if r == 0:
+                        rest = lists[k][fit:]
+                    else:
+                        rest = torch.empty(n - fit, dtype=torch.int64, device=self.buf.device)
+                        dist.recv(rest, src=r, group=self.group)
+                    piece = torch.cat([piece, rest])
+                out[k].append(piece)
+        return [torch.cat(p) for p in out]

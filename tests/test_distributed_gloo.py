@@ -21,11 +21,12 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import monkey_moore_b200.workloads as wl
     from _oracle import Oracle
-    from monkey_moore_b200.distributed import gather_offsets, shard_bytes
+    from monkey_moore_b200.distributed import PackedGather, gather_offsets, shard_bytes
 
     w = wl.WORKLOADS["cfg2"].scaled(3 << 20)
     w.block_size = 65536
     results = {}
+    mine_lists, whole_lists = [], []
     for s in w.searches:
         o = Oracle(w.bits, keyword=s.pattern["keyword"], wildcard=s.pattern["wildcard"])
         overlap = (len(s.pattern["keyword"]) - 1) * 2
@@ -35,9 +36,17 @@ def _worker(rank, world, port, out):
         # a match belongs to the block holding its first byte: drop what the next rank owns
         off = off[off < np.uint64(nb * w.block_size)] + np.uint64(lo)
         g = gather_offsets(dist, torch, torch.from_numpy(off.astype(np.int64)), rank, world)
+        mine_lists.append(torch.from_numpy(off.astype(np.int64)))
         if rank == 0:
             whole, _ = o.engine(wl.host_blob(w), w.block_size, big_endian=s.big_endian, wrap32=False)
+            whole_lists.append(whole.astype(np.int64).tolist())
             results[s.name] = (g.numpy().tolist() == whole.astype(np.int64).tolist(), len(whole))
+    # the one-collective-per-step gather, once roomy and once so small that every list spills
+    for cap in (8192, 12):
+        pg = PackedGather(dist, torch, rank, world, len(mine_lists), capacity=cap, device="cpu")
+        got = pg(mine_lists)
+        if rank == 0:
+            results["packed-%d" % cap] = ([g.tolist() for g in got] == whole_lists, sum(len(x) for x in whole_lists))
     if rank == 0:
         out.put(results)
     dist.barrier()
