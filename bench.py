@@ -159,7 +159,7 @@ def run_ours(args, w):
 
     import monkey_moore_b200 as mm
     import monkey_moore_b200.workloads as wl
-    from monkey_moore_b200.distributed import PackedGather, shard_bytes
+    from monkey_moore_b200.distributed import shard_bytes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,11 +185,17 @@ def run_ours(args, w):
     mm.set_stream(stream.cuda_stream, True)
     torch.cuda.synchronize()
 
-    gather = PackedGather(dist, torch, rank, world, len(progs)) if world > 1 else None
+    comm = None
+    if world > 1:
+        def bcast(raw):
+            t = torch.tensor(list(raw), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().tolist())
+        comm = mm.Comm(rank, world, bcast)     # the library's own NCCL communicator for the result gather
 
     def step(collect=None):
         launches, filt_ms, filt_bytes = 0, 0.0, 0
-        found = []
+        held = []
         for prog, s in zip(progs, w.searches):
             res = prog.engine_scan(blob, w.block_size, big_endian=s.big_endian, file_size=total_size,
                                    first_block=b0, num_blocks=b1 - b0)
@@ -197,13 +203,15 @@ def run_ours(args, w):
             launches += st["launches"]
             filt_ms += st["ms_filter"]
             filt_bytes += st["bytes_scanned"] + 8 * res.count
-            if world > 1 or collect is not None:
-                found.append(res.torch_offsets())
-            res.close()
+            held.append(res)
         if world > 1:
-            found = gather(found)           # ONE collective per step: all searches' offsets to rank 0
-        if collect is not None and found is not None:
-            collect.extend(found)
+            gathered = comm.gather(held, fetch=collect is not None)   # ONE grouped NCCL op per step
+            if collect is not None and gathered is not None:
+                collect.extend(torch.from_numpy(g[0].astype(np.int64)) for g in gathered)
+        elif collect is not None:
+            collect.extend(r.torch_offsets() for r in held)
+        for r in held:
+            r.close()
         return launches, filt_ms, filt_bytes
 
     def barrier():

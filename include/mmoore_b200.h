@@ -123,6 +123,27 @@ typedef struct mmg_scan_stats {
 } mmg_scan_stats;
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
 
+/* ---- multi-GPU: gather of the match lists to rank 0 over NCCL (one process per GPU) -----------------
+ * The reference's engine merges per-block results of its thread pool and sorts them
+ * (src/core/search_engine.cpp:82-102, 193-197); across GPUs ranks scan disjoint block ranges
+ * (mmg_engine_scan with first_block/num_blocks) and only the result lists travel.  Rank order equals
+ * file order, so the concatenation is already sorted.  NCCL is loaded lazily (dlopen): single-GPU
+ * users do not need it.
+ *   mmg_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller broadcasts it (any transport).
+ *   mmg_comm_create    : collective over all ranks; capacity = entries of the fixed packed buffer.
+ *   mmg_comm_gather    : collective; the `nlists` lists of one step (same nlists on every rank) go to
+ *                        rank 0 in ONE grouped NCCL operation (+ point-to-point spill when a rank's lists
+ *                        exceed the packed capacity).  *out is non-NULL on rank 0 only.  */
+typedef struct mmg_comm mmg_comm;
+typedef struct mmg_gathered mmg_gathered;
+int mmg_comm_unique_id(void *out128);
+int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, mmg_comm **out);
+void mmg_comm_destroy(mmg_comm *c);
+int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out);
+uint64_t mmg_gathered_count(const mmg_gathered *g, int list);
+int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32_t *values);
+void mmg_gathered_free(mmg_gathered *g);
+
 /* Page-locked host staging memory for file -> HBM ingestion (SearchEngine<T>::run reads the file into
  * such a buffer so that the H2D copy runs at PCIe speed).  NULL when allocation fails / no device. */
 void *mmg_host_alloc(uint64_t nbytes);

@@ -34,6 +34,8 @@ C_ABI_SYMBOLS = [
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
     "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
+    "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_gathered_count",
+    "mmg_gathered_copy", "mmg_gathered_free",
 ]
 
 _u32p = C.POINTER(C.c_uint32)
@@ -98,6 +100,14 @@ def lib():
         l.mmg_results_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
         l.mmg_set_path_override.argtypes = [C.c_int]
         l.mmg_set_stream.argtypes = [C.c_void_p, C.c_int]
+        l.mmg_comm_unique_id.argtypes = [C.c_void_p]
+        l.mmg_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
+        l.mmg_comm_destroy.argtypes = [C.c_void_p]
+        l.mmg_comm_gather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_gathered_count.restype = C.c_uint64
+        l.mmg_gathered_count.argtypes = [C.c_void_p, C.c_int]
+        l.mmg_gathered_copy.argtypes = [C.c_void_p, C.c_int, _u64p, _u32p]
+        l.mmg_gathered_free.argtypes = [C.c_void_p]
         l.mmg_synth_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
         _lib = l
     return _lib
@@ -189,6 +199,53 @@ class Results:
         """The equivalency_map of every match, as the reference's ``result_type::second``."""
         _, val = self.arrays()
         return [self._program.table(int(v[0]), int(v[1])) for v in val]
+
+
+class Comm:
+    """NCCL communicator of the C-ABI for the result gather (one process per GPU).
+
+    ``Comm(rank, world, broadcast_bytes)``: ``broadcast_bytes(b)`` must return rank 0's 128-byte id on every
+    rank (e.g. via torch.distributed).  ``gather(results_list)`` -> on rank 0 a list of (offsets, values)
+    numpy pairs per search (``fetch=True``) or the per-search counts; ``None`` elsewhere."""
+
+    def __init__(self, rank, world, broadcast_bytes, capacity=8192):
+        self.rank, self.world = rank, world
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().mmg_comm_unique_id(ident))
+        raw = broadcast_bytes(bytes(ident.raw))
+        h = C.c_void_p()
+        _check(lib().mmg_comm_create(C.create_string_buffer(raw, 128), rank, world, int(capacity), C.byref(h)))
+        self._h = h
+
+    def gather(self, results, fetch=False):
+        n = len(results)
+        arr = (C.c_void_p * n)(*[r._h for r in results])
+        g = C.c_void_p()
+        _check(lib().mmg_comm_gather(self._h, arr, n, C.byref(g)))
+        if not g:
+            return None
+        try:
+            counts = [int(lib().mmg_gathered_count(g, k)) for k in range(n)]
+            if not fetch:
+                return counts
+            out = []
+            for k in range(n):
+                off = np.zeros(counts[k], np.uint64)
+                val = np.zeros((counts[k], 2), np.uint32)
+                if counts[k]:
+                    _check(lib().mmg_gathered_copy(g, k, off.ctypes.data_as(_u64p), val.ctypes.data_as(_u32p)))
+                out.append((off, val))
+            return out
+        finally:
+            lib().mmg_gathered_free(g)
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mmg_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 class Program:

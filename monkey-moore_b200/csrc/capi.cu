@@ -440,6 +440,19 @@ void mmg_results_free(mmg_results *r) {
     delete r;
 }
 
+// internal doorways for comm.cu (not part of the public header)
+struct mmg_results_view { uint64_t count; const uint64_t *d_off; const uint32_t *d_val; };
+int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out) {
+    out->count = r ? r->count : 0;
+    out->d_off = r ? r->d_off : nullptr;
+    out->d_val = r ? r->d_val : nullptr;
+    return MMG_OK;
+}
+void *mmg_internal_stream(void) {
+    try { return device_info().stream; } catch (const ScanError &) { return nullptr; }
+}
+void mmg_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+
 void *mmg_host_alloc(uint64_t nbytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -335,7 +335,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t warp = blockIdx.x * MMG_FILTER_WARPS + wib;
-    const uint32_t nwarps = gridDim.x * MMG_FILTER_WARPS;
     const uint32_t reg_lo = warp * X.ev_per_warp;
     // window start = first byte of the current element of comparison 0, minus sigma
     const int64_t sigma = (LB == 0) ? 0 : (int64_t)P.chk[0].i * W;
