@@ -195,15 +195,16 @@ def run_ours(args, w):
 
     def step(collect=None):
         launches, filt_ms, filt_bytes = 0, 0.0, 0
-        held = []
-        for prog, s in zip(progs, w.searches):
-            res = prog.engine_scan(blob, w.block_size, big_endian=s.big_endian, file_size=total_size,
-                                   first_block=b0, num_blocks=b1 - b0)
+        # the searches of a step are independent: enqueue them all, then complete them (the host work of
+        # one overlaps the GPU work of the other)
+        held = [prog.engine_scan(blob, w.block_size, big_endian=s.big_endian, file_size=total_size,
+                                 first_block=b0, num_blocks=b1 - b0, asynchronous=True)
+                for prog, s in zip(progs, w.searches)]
+        for res in held:
             st = res.stats()
             launches += st["launches"]
             filt_ms += st["ms_filter"]
             filt_bytes += st["bytes_scanned"] + 8 * res.count
-            held.append(res)
         if world > 1:
             gathered = comm.gather(held, fetch=collect is not None)   # ONE grouped NCCL op per step
             if collect is not None and gathered is not None:

@@ -97,6 +97,15 @@ int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, in
                     uint64_t file_size, uint32_t block_size, uint64_t first_block, uint64_t num_blocks,
                     int big_endian, mmg_results **out);
 
+/* Asynchronous form: enqueues the scan on the calling thread's stream and returns at once with a
+ * PENDING results object, so that the host work of the next scan overlaps the GPU work of this one.
+ * mmg_results_wait() (or any accessor, or mmg_results_free) completes it and returns its status.  The
+ * input bytes must stay valid until then. */
+int mmg_engine_scan_async(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem,
+                          uint64_t file_size, uint32_t block_size, uint64_t first_block, uint64_t num_blocks,
+                          int big_endian, mmg_results **out);
+int mmg_results_wait(mmg_results *r);
+
 /* Number of blocks compute_search_blocks() produces (== number of per-block progress callbacks,
  * tests/test_search_engine.cpp:376-396). */
 uint64_t mmg_num_blocks(uint64_t file_size, uint32_t block_size);

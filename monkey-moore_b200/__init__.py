@@ -31,7 +31,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 C_ABI_SYMBOLS = [
     "mmg_last_error", "mmg_device_count", "mmg_program_create_keyword", "mmg_program_create_values",
     "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
-    "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_num_blocks", "mmg_results_count",
+    "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_engine_scan_async", "mmg_results_wait", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
     "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
     "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_gathered_count",
@@ -87,6 +87,8 @@ def lib():
         l.mmg_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
         l.mmg_engine_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint32,
                                       C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_engine_scan_async.argtypes = l.mmg_engine_scan.argtypes
+        l.mmg_results_wait.argtypes = [C.c_void_p]
         l.mmg_num_blocks.restype = C.c_uint64
         l.mmg_num_blocks.argtypes = [C.c_uint64, C.c_uint32]
         l.mmg_results_count.restype = C.c_uint64
@@ -148,10 +150,24 @@ def device_count():
 class Results:
     """Match list of one scan (device resident until freed)."""
 
-    def __init__(self, handle, program):
+    def __init__(self, handle, program, keep=None):
         self._h = handle
         self._program = program
-        self.count = int(lib().mmg_results_count(handle))
+        self._keep = keep          # input buffer of an asynchronous scan: must outlive it
+        self._count = None
+
+    def wait(self):
+        """Completes an asynchronous scan (no-op otherwise)."""
+        _check(lib().mmg_results_wait(self._h))
+        self._keep = None
+        return self
+
+    @property
+    def count(self):
+        if self._count is None:
+            self.wait()
+            self._count = int(lib().mmg_results_count(self._h))
+        return self._count
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -304,15 +320,18 @@ class Program:
         _check(lib().mmg_search(self._h, ptr, nbytes // (self.bits // 8), mem, C.byref(h)))
         return Results(h, self)
 
-    def engine_scan(self, data, block_size, big_endian=False, file_size=None, first_block=0, num_blocks=0):
-        """The chunk engine of ``SearchEngine<T>::run`` over a file image (or one rank's slice of it)."""
+    def engine_scan(self, data, block_size, big_endian=False, file_size=None, first_block=0, num_blocks=0,
+                    asynchronous=False):
+        """The chunk engine of ``SearchEngine<T>::run`` over a file image (or one rank's slice of it).
+        ``asynchronous=True`` only enqueues the scan; the returned Results completes on first use / wait()."""
         ptr, nbytes, mem, keep = self._pointer(data)
         if file_size is None:
             file_size = nbytes
         h = C.c_void_p()
-        _check(lib().mmg_engine_scan(self._h, ptr, nbytes, mem, int(file_size), int(block_size), int(first_block),
-                                     int(num_blocks), int(bool(big_endian)), C.byref(h)))
-        return Results(h, self)
+        fn = lib().mmg_engine_scan_async if asynchronous else lib().mmg_engine_scan
+        _check(fn(self._h, ptr, nbytes, mem, int(file_size), int(block_size), int(first_block),
+                  int(num_blocks), int(bool(big_endian)), C.byref(h)))
+        return Results(h, self, keep if asynchronous else None)
 
 
 class MonkeyMoore:

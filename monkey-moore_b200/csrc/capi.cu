@@ -84,16 +84,6 @@ struct Arena {
 
 }  // namespace
 
-struct mmg_results {
-    uint64_t count = 0;
-    uint64_t *d_off = nullptr;
-    uint32_t *d_val = nullptr;
-    cudaStream_t stream = nullptr;
-    mmg_scan_stats stats{};
-};
-
-namespace {
-
 struct ScanRequest {
     const mmg_program *prog;
     const uint8_t *d_bytes;   // device
@@ -106,7 +96,72 @@ struct ScanRequest {
     uint32_t report_shift;
 };
 
-void run_generic(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results *res, uint32_t &launches) {
+// what a launched-but-not-yet-finished tiled scan needs to be completed (or re-run after an overflow)
+struct TiledState {
+    MmgGeom G{};
+    MmgScratch X{};
+    int lag_bytes = 0, grid = 0;
+    uint64_t total_warps = 0, per_warp = 0, cap = 0;
+    uint8_t *base = nullptr;
+    size_t zero_bytes = 0;
+};
+
+struct mmg_results {
+    uint64_t count = 0;
+    uint64_t *d_off = nullptr;
+    uint32_t *d_val = nullptr;
+    cudaStream_t stream = nullptr;
+    mmg_scan_stats stats{};
+    // ---- in-flight state (mmg_*_async): completed by finish_scan()
+    bool pending = false;
+    int error = MMG_OK;
+    bool tiled = false, from_host = false;
+    ScanRequest rq{};
+    TiledState t;
+    Arena *arena = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after H2D, after filter, end
+    uint64_t *status_host = nullptr;                            // pinned slot receiving X.status
+    uint32_t launches = 0;
+};
+
+namespace {
+
+// small pools shared by all threads: CUDA events and pinned status slots are expensive to create per scan
+std::mutex g_pool_mutex;
+std::vector<cudaEvent_t> g_event_pool;
+std::vector<uint64_t *> g_slot_pool;
+
+cudaEvent_t take_event() {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    }
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    return e;
+}
+
+uint64_t *take_slot() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_slot_pool.empty()) {
+        uint64_t *block = nullptr;
+        CU(cudaHostAlloc((void **)&block, 64 * 8 * sizeof(uint64_t), cudaHostAllocDefault));
+        for (int i = 0; i < 64; i++) g_slot_pool.push_back(block + 8 * i);
+    }
+    uint64_t *s = g_slot_pool.back();
+    g_slot_pool.pop_back();
+    return s;
+}
+
+void release_inflight(mmg_results *r) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (auto &e : r->ev) { if (e) g_event_pool.push_back(e); e = nullptr; }
+    if (r->status_host) { g_slot_pool.push_back(r->status_host); r->status_host = nullptr; }
+    delete r->arena;
+    r->arena = nullptr;
+}
+
+void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_results *res, uint32_t &launches) {
     const MmgProgram &P = rq.prog->dev;
     MmgGeom G{};
     G.data = rq.d_bytes; G.S = rq.S; G.B = rq.B; G.base_offset = rq.base_offset;
@@ -119,36 +174,55 @@ void run_generic(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_resul
     uint64_t *bases = arena.get<uint64_t>(n);
     uint64_t *bsum = arena.get<uint64_t>((n + 1023) / 1024 + 1);
     uint64_t *total_d = arena.get<uint64_t>(1);
-    CU(mmg_launch_generic_walk(P, G, counts, nullptr, nullptr, nullptr, dev.stream));
-    CU(mmg_launch_scan(counts, n, bsum, bases, total_d, dev.stream));
+    CU(mmg_launch_generic_walk(P, G, counts, nullptr, nullptr, nullptr, stream));
+    CU(mmg_launch_scan(counts, n, bsum, bases, total_d, stream));
     launches += 4;
     uint64_t total = 0;
-    CU(cudaMemcpyAsync(&total, total_d, sizeof(total), cudaMemcpyDeviceToHost, dev.stream));
-    CU(cudaStreamSynchronize(dev.stream));
+    CU(cudaMemcpyAsync(&total, total_d, sizeof(total), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
     res->count = total;
     if (total == 0) return;
-    CU(cudaMallocAsync((void **)&res->d_off, total * sizeof(uint64_t), dev.stream));
-    CU(cudaMallocAsync((void **)&res->d_val, total * sizeof(uint32_t), dev.stream));
+    CU(cudaMallocAsync((void **)&res->d_off, total * sizeof(uint64_t), stream));
+    CU(cudaMallocAsync((void **)&res->d_val, total * sizeof(uint32_t), stream));
     if (rq.npads == 1) {
-        CU(mmg_launch_generic_walk(P, G, counts, bases, res->d_off, res->d_val, dev.stream));
+        CU(mmg_launch_generic_walk(P, G, counts, bases, res->d_off, res->d_val, stream));
         launches += 1;
     } else {
         uint64_t *tmp_off = arena.get<uint64_t>(total);
         uint32_t *tmp_val = arena.get<uint32_t>(total);
-        CU(mmg_launch_generic_walk(P, G, counts, bases, tmp_off, tmp_val, dev.stream));
-        CU(mmg_launch_generic_merge(G.nblocks, counts, bases, tmp_off, tmp_val, res->d_off, res->d_val, dev.stream));
+        CU(mmg_launch_generic_walk(P, G, counts, bases, tmp_off, tmp_val, stream));
+        CU(mmg_launch_generic_merge(G.nblocks, counts, bases, tmp_off, tmp_val, res->d_off, res->d_val, stream));
         launches += 2;
     }
 }
 
-void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results *res, uint32_t &launches,
-               cudaEvent_t ev_filter_done) {
-    const MmgProgram &P = rq.prog->dev;
-    const int W = P.W;
-    int lag_bytes = (P.ncheck > 0 && P.nkeys >= 0) ? P.chk[0].lag * W : 0;
-    if (!mmg_filter_supported(W, lag_bytes) || g_path_override == 2) lag_bytes = 0;   // evaluate every window exactly
+// enqueues one attempt of the tiled pipeline: zero scratch, filter, maps, phases+walk, scan+emit, status D2H
+void enqueue_tiled(mmg_results *res, bool record_filter_event) {
+    const MmgProgram &P = res->rq.prog->dev;
+    TiledState &t = res->t;
+    cudaStream_t stream = res->stream;
+    t.X.ev_per_warp = (uint32_t)t.per_warp;
+    t.X.ev = res->arena->get<uint32_t>(t.per_warp * t.total_warps);
+    CU(cudaMemsetAsync(t.base, 0, t.zero_bytes, stream));
+    CU(mmg_launch_filter(P, t.G, t.X, t.lag_bytes, t.grid, stream));
+    if (record_filter_event) CU(cudaEventRecord(res->ev[2], stream));
+    CU(mmg_launch_maps(P, t.G, t.X, stream));
+    CU(mmg_launch_phases_walk(P, t.G, t.X, stream));
+    CU(mmg_launch_scan_emit(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
+    res->launches += 4;
+    CU(cudaMemcpyAsync(res->status_host, t.X.status, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+}
 
-    MmgGeom G{};
+void launch_tiled(mmg_results *res, DeviceInfo &dev) {
+    const ScanRequest &rq = res->rq;
+    const MmgProgram &P = rq.prog->dev;
+    TiledState &t = res->t;
+    Arena &arena = *res->arena;
+    const int W = P.W;
+    t.lag_bytes = (P.ncheck > 0 && P.nkeys >= 0) ? P.chk[0].lag * W : 0;
+    if (!mmg_filter_supported(W, t.lag_bytes) || g_path_override == 2) t.lag_bytes = 0;   // evaluate every window exactly
+
+    MmgGeom &G = t.G;
     G.data = rq.d_bytes; G.S = rq.S; G.base_offset = rq.base_offset;
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * W; G.npads = rq.npads;
     G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
@@ -162,93 +236,119 @@ void run_tiled(const ScanRequest &rq, DeviceInfo &dev, Arena &arena, mmg_results
     G.nsub = (uint32_t)nsub64;
 
     int occ = 1;
-    CU(mmg_filter_occupancy(W, lag_bytes, rq.big_endian, P.nkeys, &occ));
-    const int grid = dev.sms * std::max(occ, 1);
-    const uint64_t total_warps = (uint64_t)grid * 8;
+    CU(mmg_filter_occupancy(W, t.lag_bytes, rq.big_endian, P.nkeys, &occ));
+    t.grid = dev.sms * std::max(occ, 1);
+    t.total_warps = (uint64_t)t.grid * 8;
     uint32_t cs = 8;   // sub-tiles per chunk: small enough that dynamic scheduling balances the tail
-    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 8 * total_warps)) cs >>= 1;
+    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 8 * t.total_warps)) cs >>= 1;
     G.chunk_subs = cs;
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
 
-    MmgScratch X{};
+    MmgScratch &X = t.X;
     const uint32_t npads = rq.npads;
     X.jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
-
     // one allocation for all per-scan scratch; the zero-initialised part comes first
     const uint32_t ntiles = (G.nsub + 255) / 256;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
     const size_t o_status = carve(4 * sizeof(uint64_t));
-    const size_t o_ticket = carve(sizeof(uint32_t));
+    const size_t o_ticket = carve(2 * sizeof(uint32_t));
     const size_t o_lookback = carve((size_t)ntiles * sizeof(uint64_t));
     const size_t o_chain = carve((size_t)G.nblocks * npads);
-    const size_t zero_bytes = off;
+    const size_t o_hasmap = carve((size_t)G.nsub * npads);
+    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
+    t.zero_bytes = off;
     const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_hasmap = carve((size_t)G.nsub * npads);
+    const size_t o_nonempty = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_maps = carve((size_t)G.nsub * npads * X.jp);
-    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
     uint8_t *base = arena.get<uint8_t>(off);
+    t.base = base;
     X.status = reinterpret_cast<uint64_t *>(base + o_status);
     X.ticket = reinterpret_cast<uint32_t *>(base + o_ticket);
+    X.n_nonempty = X.ticket + 1;
     X.lookback = reinterpret_cast<uint64_t *>(base + o_lookback);
     X.chain_has = base + o_chain;
+    X.hasmap = base + o_hasmap;
+    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
     X.sub_start = reinterpret_cast<uint32_t *>(base + o_start);
     X.sub_count = reinterpret_cast<uint32_t *>(base + o_count);
-    X.hasmap = base + o_hasmap;
+    X.nonempty = reinterpret_cast<uint32_t *>(base + o_nonempty);
     X.maps = base + o_maps;
-    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
     X.mbase = reinterpret_cast<uint64_t *>(base + o_mbase);
 
     // optimistic result capacity: what this pattern produced last time plus slack
-    uint64_t cap = std::max<uint64_t>(4096, rq.prog->last_count + rq.prog->last_count / 4 + 1024);
-    CU(cudaMallocAsync((void **)&res->d_off, cap * sizeof(uint64_t), dev.stream));
-    CU(cudaMallocAsync((void **)&res->d_val, cap * sizeof(uint32_t), dev.stream));
+    t.cap = std::max<uint64_t>(4096, rq.prog->last_count + rq.prog->last_count / 4 + 1024);
+    CU(cudaMallocAsync((void **)&res->d_off, t.cap * sizeof(uint64_t), res->stream));
+    CU(cudaMallocAsync((void **)&res->d_val, t.cap * sizeof(uint32_t), res->stream));
 
     // event capacity: private, equally sized regions per filter warp; grown and re-run on overflow
-    uint64_t per_warp = std::max<uint64_t>(256, rq.S / 8 / total_warps);
-    if (rq.prog->last_events_per_warp) per_warp = std::max<uint64_t>(256, rq.prog->last_events_per_warp * 2);
-    if (lag_bytes == 0) per_warp = std::max<uint64_t>(per_warp, (rq.S / total_warps + MMG_SUBTILE) * 2);
-    uint64_t status[4] = {0, 0, 0, 0};
-    for (int attempt = 0;; attempt++) {
-        if (per_warp * total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
-        X.ev_per_warp = (uint32_t)per_warp;
-        X.ev = arena.get<uint32_t>(per_warp * total_warps);
-        CU(cudaMemsetAsync(base, 0, zero_bytes, dev.stream));
-        CU(mmg_launch_filter(P, G, X, lag_bytes, grid, dev.stream));
-        if (attempt == 0) CU(cudaEventRecord(ev_filter_done, dev.stream));
-        CU(mmg_launch_maps(P, G, X, dev.stream));
-        CU(mmg_launch_phases_walk(P, G, X, dev.stream));
-        CU(mmg_launch_scan_emit(P, G, X, res->d_off, res->d_val, cap, dev.stream));
-        launches += 4;
-        CU(cudaMemcpyAsync(status, X.status, sizeof(status), cudaMemcpyDeviceToHost, dev.stream));
-        CU(cudaStreamSynchronize(dev.stream));
-        if (status[0] <= per_warp) break;
+    t.per_warp = std::max<uint64_t>(256, rq.S / 8 / t.total_warps);
+    if (rq.prog->last_events_per_warp) t.per_warp = std::max<uint64_t>(256, rq.prog->last_events_per_warp * 2);
+    if (t.lag_bytes == 0) t.per_warp = std::max<uint64_t>(t.per_warp, (rq.S / t.total_warps + MMG_SUBTILE) * 2);
+    if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
+    enqueue_tiled(res, true);
+}
+
+// completes a tiled scan: waits, re-runs with exact sizes when an optimistic buffer was too small
+void finish_tiled(mmg_results *res) {
+    const MmgProgram &P = res->rq.prog->dev;
+    TiledState &t = res->t;
+    cudaStream_t stream = res->stream;
+    CU(cudaEventSynchronize(res->ev[3]));
+    uint64_t *status = res->status_host;
+    for (int attempt = 0; status[0] > t.per_warp; attempt++) {
         if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
-        per_warp = status[0] + status[0] / 4 + 64;
+        t.per_warp = status[0] + status[0] / 4 + 64;
+        if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
+        enqueue_tiled(res, false);
+        CU(cudaEventRecord(res->ev[3], stream));
+        CU(cudaStreamSynchronize(stream));
     }
-    rq.prog->last_events_per_warp = status[0];
-    rq.prog->last_count = status[2];
+    res->rq.prog->last_events_per_warp = status[0];
+    res->rq.prog->last_count = status[2];
     res->stats.events = status[1];
     res->count = status[2];
-    if (res->count > cap) {
+    if (res->count > t.cap) {
         // the optimistic buffer was too small: allocate exactly and emit again from the stored bases
-        CU(cudaFreeAsync(res->d_off, dev.stream));
-        CU(cudaFreeAsync(res->d_val, dev.stream));
+        CU(cudaFreeAsync(res->d_off, stream));
+        CU(cudaFreeAsync(res->d_val, stream));
         res->d_off = nullptr; res->d_val = nullptr;
-        CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), dev.stream));
-        CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), dev.stream));
-        CU(mmg_launch_emit(P, G, X, res->d_off, res->d_val, dev.stream));
-        launches += 1;
+        CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), stream));
+        CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), stream));
+        CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
+        res->launches += 1;
+        CU(cudaEventRecord(res->ev[3], stream));
+        CU(cudaStreamSynchronize(stream));
     }
 }
 
-int run_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
-             uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, mmg_results **out) {
+// Blocks until the scan behind `r` is complete; returns its status code.
+int finish_scan(mmg_results *r) {
+    if (!r->pending) return r->error;
+    r->pending = false;
+    try {
+        if (r->tiled) finish_tiled(r);
+        else CU(cudaEventSynchronize(r->ev[3]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1])); r->stats.ms_h2d = r->from_host ? ms : 0.f;
+        CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
+        CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[3])); r->stats.ms_total = ms;
+        r->stats.launches = r->launches;
+    } catch (const ScanError &e) {
+        r->error = e.code;
+        cudaGetLastError();
+    }
+    release_inflight(r);
+    return r->error;
+}
+
+// Enqueues a scan on the calling thread's stream; *out is a pending results object.
+int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
+                uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, mmg_results **out) {
     *out = nullptr;
     mmg_results *res = new mmg_results();
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
     try {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -257,47 +357,49 @@ int run_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int me
         res->stream = dev.stream;
         res->stats.bytes_scanned = nbytes;
         if (nbytes == 0 || nblocks == 0) { *out = res; return MMG_OK; }
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventCreate(&e3));
-        uint32_t launches = 0;
-        {
-            Arena arena(dev.stream);
-            const uint8_t *d_bytes = static_cast<const uint8_t *>(bytes);
-            CU(cudaEventRecord(e0, dev.stream));
-            if (mem == MMG_MEM_HOST) {
-                uint8_t *buf = arena.get<uint8_t>(nbytes + 16);
-                CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, dev.stream));
-                d_bytes = buf;
-            } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
-                throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
-            }
-            CU(cudaEventRecord(e1, dev.stream));
-
-            ScanRequest rq{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
-            const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
-            const bool tiled = regular && g_path_override != 1;
-            res->stats.fast_path = tiled;
-            if (tiled) run_tiled(rq, dev, arena, res, launches, e2);
-            else { run_generic(rq, dev, arena, res, launches); CU(cudaEventRecord(e2, dev.stream)); }
-            CU(cudaEventRecord(e3, dev.stream));
-            CU(cudaStreamSynchronize(dev.stream));
+        for (auto &e : res->ev) e = take_event();
+        res->status_host = take_slot();
+        res->arena = new Arena(dev.stream);
+        res->from_host = mem == MMG_MEM_HOST;
+        const uint8_t *d_bytes = static_cast<const uint8_t *>(bytes);
+        CU(cudaEventRecord(res->ev[0], dev.stream));
+        if (mem == MMG_MEM_HOST) {
+            uint8_t *buf = res->arena->get<uint8_t>(nbytes + 16);
+            CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, dev.stream));
+            d_bytes = buf;
+        } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
+            throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
         }
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, e0, e1)); res->stats.ms_h2d = mem == MMG_MEM_HOST ? ms : 0.f;
-        CU(cudaEventElapsedTime(&ms, e1, e2)); res->stats.ms_filter = ms;
-        CU(cudaEventElapsedTime(&ms, e1, e3)); res->stats.ms_total = ms;
-        res->stats.launches = launches;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+        CU(cudaEventRecord(res->ev[1], dev.stream));
+        res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
+        const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
+        res->tiled = regular && g_path_override != 1;
+        res->stats.fast_path = res->tiled;
+        if (res->tiled) {
+            launch_tiled(res, dev);
+        } else {
+            run_generic(res->rq, dev.stream, *res->arena, res, res->launches);
+            CU(cudaEventRecord(res->ev[2], dev.stream));
+        }
+        CU(cudaEventRecord(res->ev[3], dev.stream));
+        res->pending = true;
         *out = res;
         return MMG_OK;
     } catch (const ScanError &e) {
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        if (e2) cudaEventDestroy(e2);
-        if (e3) cudaEventDestroy(e3);
-        mmg_results_free(res);
         cudaGetLastError();
+        release_inflight(res);
+        mmg_results_free(res);
         return e.code;
     }
+}
+
+int run_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
+             uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, bool async, mmg_results **out) {
+    int rc = launch_scan(prog, bytes, nbytes, mem, B, nblocks, npads, big_endian, base_offset, report_shift, out);
+    if (rc != MMG_OK || async) return rc;
+    rc = finish_scan(*out);
+    if (rc != MMG_OK) { mmg_results_free(*out); *out = nullptr; }
+    return rc;
 }
 
 }  // namespace
@@ -393,12 +495,12 @@ int mmg_search(const mmg_program *p, const void *data, uint64_t data_len, int me
     if (!p || !out || (!data && data_len)) return fail(MMG_ERR_ARG, "null argument");
     const uint32_t W = p->dev.W;
     const uint64_t nbytes = data_len * W;
-    return run_scan(p, data, nbytes, mem, nbytes, nbytes ? 1 : 0, 1, false, 0, W == 2 ? 1 : 0, out);
+    return run_scan(p, data, nbytes, mem, nbytes, nbytes ? 1 : 0, 1, false, 0, W == 2 ? 1 : 0, false, out);
 }
 
-int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
-                    uint32_t block_size, uint64_t first_block, uint64_t num_blocks, int big_endian,
-                    mmg_results **out) {
+static int engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
+                       uint32_t block_size, uint64_t first_block, uint64_t num_blocks, int big_endian, bool async,
+                       mmg_results **out) {
     if (!p || !out || (!bytes && nbytes)) return fail(MMG_ERR_ARG, "null argument");
     if (block_size == 0) return fail(MMG_ERR_ARG, "block_size must be positive");
     const uint64_t all_blocks = mmg_num_blocks(file_size, block_size);
@@ -409,12 +511,38 @@ int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, in
     const uint64_t base = first_block * (uint64_t)block_size;
     uint64_t need = std::min<uint64_t>(file_size - std::min(base, file_size), num_blocks * (uint64_t)block_size + ov);
     if (nbytes < need) return fail(MMG_ERR_ARG, "slice shorter than the blocks it must cover");
-    return run_scan(p, bytes, need, mem, block_size, num_blocks, W, big_endian != 0 && W == 2, base, 0, out);
+    return run_scan(p, bytes, need, mem, block_size, num_blocks, W, big_endian != 0 && W == 2, base, 0, async, out);
 }
 
-uint64_t mmg_results_count(const mmg_results *r) { return r ? r->count : 0; }
+int mmg_engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
+                    uint32_t block_size, uint64_t first_block, uint64_t num_blocks, int big_endian,
+                    mmg_results **out) {
+    return engine_scan(p, bytes, nbytes, mem, file_size, block_size, first_block, num_blocks, big_endian, false, out);
+}
+
+int mmg_engine_scan_async(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
+                          uint32_t block_size, uint64_t first_block, uint64_t num_blocks, int big_endian,
+                          mmg_results **out) {
+    return engine_scan(p, bytes, nbytes, mem, file_size, block_size, first_block, num_blocks, big_endian, true, out);
+}
+
+int mmg_results_wait(mmg_results *r) {
+    if (!r) return fail(MMG_ERR_ARG, "null results");
+    return finish_scan(r);
+}
+
+// every accessor completes a pending scan first
+static mmg_results *done(const mmg_results *r) {
+    mmg_results *m = const_cast<mmg_results *>(r);
+    if (m && m->pending) finish_scan(m);
+    return m;
+}
+
+uint64_t mmg_results_count(const mmg_results *r) { return r ? done(r)->count : 0; }
 
 int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t *offsets, uint32_t *values) {
+    if (r) done(r);
+    if (r && r->error != MMG_OK) return r->error;
     if (!r || first + n > r->count) return fail(MMG_ERR_ARG, "range outside the result list");
     if (n == 0) return MMG_OK;
     if (offsets) {
@@ -430,11 +558,12 @@ int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t 
     return MMG_OK;
 }
 
-const uint64_t *mmg_results_device_offsets(const mmg_results *r) { return r ? r->d_off : nullptr; }
-const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? r->d_val : nullptr; }
+const uint64_t *mmg_results_device_offsets(const mmg_results *r) { return r ? done(r)->d_off : nullptr; }
+const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? done(r)->d_val : nullptr; }
 
 void mmg_results_free(mmg_results *r) {
     if (!r) return;
+    if (r->pending) finish_scan(r);
     if (r->d_off) cudaFreeAsync(r->d_off, r->stream);
     if (r->d_val) cudaFreeAsync(r->d_val, r->stream);
     delete r;
@@ -443,6 +572,7 @@ void mmg_results_free(mmg_results *r) {
 // internal doorways for comm.cu (not part of the public header)
 struct mmg_results_view { uint64_t count; const uint64_t *d_off; const uint32_t *d_val; };
 int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out) {
+    if (r) done(r);
     out->count = r ? r->count : 0;
     out->d_off = r ? r->d_off : nullptr;
     out->d_val = r ? r->d_val : nullptr;
@@ -482,6 +612,7 @@ int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t fi
 
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out) {
     if (!r || !out) return fail(MMG_ERR_ARG, "null argument");
+    done(r);
     *out = r->stats;
     return MMG_OK;
 }

@@ -210,14 +210,16 @@ struct WarpState {
 };
 
 __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState st, uint32_t t, int lane) {
-    while (st.open_t < t) {
+    // only sub-tiles that own events are recorded (extent + an entry in the non-empty list)
+    if (st.open_t < t && st.cursor != st.open_start) {
         if (lane == 0) {
             X.sub_start[st.open_t] = st.open_start;
             X.sub_count[st.open_t] = st.cursor - st.open_start;
+            X.nonempty[atomicAdd(X.n_nonempty, 1u)] = st.open_t;
         }
         st.open_start = st.cursor;
-        st.open_t++;
     }
+    if (st.open_t < t) st.open_t = t;
     return st;
 }
 
@@ -485,20 +487,18 @@ __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint
     return x - n;
 }
 
+// one thread per sub-tile that owns events (grid-stride over the non-empty list)
 __global__ void __launch_bounds__(128)
 k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G.nsub || events_overflowed(X)) return;
-    const uint32_t n = X.sub_count[t];
+    if (events_overflowed(X)) return;
+    const uint32_t total = *X.n_nonempty;
     const uint32_t W = P.W, npads = G.npads;
-    X.mcount[t] = 0;
-    if (n == 0) {
-        for (uint32_t c = 0; c < npads; c++) X.hasmap[t * npads + c] = 0;
-        return;
-    }
-    const uint32_t *ev = X.ev + X.sub_start[t];
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
     uint32_t x[MMG_MAXL];
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t t = X.nonempty[idx];
+    const uint32_t n = X.sub_count[t];
+    const uint32_t *ev = X.ev + X.sub_start[t];
     for (uint32_t c = 0; c < npads; c++) {
         for (uint32_t e = 0; e < Jmax; e++) x[e] = e;
         bool any = false;
@@ -512,12 +512,13 @@ k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
                 if (xe <= q && (J0 == 1 || (q - xe) % J0 == 0)) x[e] = q + j;
             }
         }
-        X.hasmap[t * npads + c] = any;
         if (any) {
+            X.hasmap[t * npads + c] = 1;                   // hasmap / mcount were zeroed by the host
             X.chain_has[(t / G.spb) * npads + c] = 1;      // benign race: every writer stores 1
             uint8_t *m = X.maps + (size_t)(t * npads + c) * X.jp;
             for (uint32_t e = 0; e < Jmax; e++) m[e] = (uint8_t)lattice_advance(x[e], NP, J0);
         }
+    }
     }
 }
 
@@ -873,7 +874,8 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
 }
 
 cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
-    k_maps<<<(G.nsub + 127) / 128, 128, 0, stream>>>(P, G, X);
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)G.nsub + 127) / 128, 148ull * 8);
+    k_maps<<<grid, 128, 0, stream>>>(P, G, X);
     return cudaGetLastError();
 }
 

@@ -55,16 +55,18 @@ struct MmgGeom {
 struct MmgScratch {
     uint32_t *ev;          // event words, one private region per filter warp
     uint32_t ev_per_warp;
-    uint32_t *sub_start;   // [nsub] first event of the sub-tile
-    uint32_t *sub_count;   // [nsub]
-    uint8_t *hasmap;       // [nsub*npads]
+    uint32_t *sub_start;   // [nsub] first event of the sub-tile (valid where the sub-tile owns events)
+    uint32_t *sub_count;   // [nsub] ditto
+    uint8_t *hasmap;       // [nsub*npads] (zeroed by the host)
     uint8_t *maps;         // [nsub*npads*jp]
     uint8_t *chain_has;    // [nblocks*npads] chain has at least one event (zeroed by the host)
-    uint32_t *mcount;      // [nsub] visited matches
+    uint32_t *mcount;      // [nsub] visited matches (zeroed by the host)
     uint64_t *mbase;       // [nsub] exclusive prefix of mcount
     uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches [3] next chunk (dynamic scheduling)
     uint64_t *lookback;    // [ceil(nsub/256)] decoupled look-back words of the match-count scan (zeroed by the host)
     uint32_t *ticket;      // tile ticket of the scan (zeroed by the host)
+    uint32_t *n_nonempty;  // number of sub-tiles that own events (zeroed by the host)
+    uint32_t *nonempty;    // [nsub] their indices, in completion order
     uint32_t jp;           // bytes per map (Jmax rounded up to 16)
 };
 
