@@ -206,10 +206,8 @@ void enqueue_tiled(mmg_results *res, bool record_filter_event) {
     CU(cudaMemsetAsync(t.base, 0, t.zero_bytes, stream));
     CU(mmg_launch_filter(P, t.G, t.X, t.lag_bytes, t.grid, stream));
     if (record_filter_event) CU(cudaEventRecord(res->ev[2], stream));
-    CU(mmg_launch_maps(P, t.G, t.X, stream));
-    CU(mmg_launch_phases_walk(P, t.G, t.X, stream));
-    CU(mmg_launch_scan_emit(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
-    res->launches += 4;
+    CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
+    res->launches += 2;
     CU(cudaMemcpyAsync(res->status_host, t.X.status, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
 }
 
@@ -245,37 +243,27 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev) {
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
 
     MmgScratch &X = t.X;
-    const uint32_t npads = rq.npads;
-    X.jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
     // one allocation for all per-scan scratch; the zero-initialised part comes first
-    const uint32_t ntiles = (G.nsub + 255) / 256;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
     const size_t o_status = carve(4 * sizeof(uint64_t));
-    const size_t o_ticket = carve(2 * sizeof(uint32_t));
-    const size_t o_lookback = carve((size_t)ntiles * sizeof(uint64_t));
-    const size_t o_chain = carve((size_t)G.nblocks * npads);
-    const size_t o_hasmap = carve((size_t)G.nsub * npads);
-    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_ticket = carve(sizeof(uint32_t));
+    const size_t o_lookback = carve((size_t)G.nblocks * sizeof(uint64_t));
+    const size_t o_hasev = carve((size_t)G.nsub);
     t.zero_bytes = off;
     const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_nonempty = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_maps = carve((size_t)G.nsub * npads * X.jp);
+    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
     uint8_t *base = arena.get<uint8_t>(off);
     t.base = base;
     X.status = reinterpret_cast<uint64_t *>(base + o_status);
     X.ticket = reinterpret_cast<uint32_t *>(base + o_ticket);
-    X.n_nonempty = X.ticket + 1;
     X.lookback = reinterpret_cast<uint64_t *>(base + o_lookback);
-    X.chain_has = base + o_chain;
-    X.hasmap = base + o_hasmap;
-    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
+    X.hasev = base + o_hasev;
     X.sub_start = reinterpret_cast<uint32_t *>(base + o_start);
     X.sub_count = reinterpret_cast<uint32_t *>(base + o_count);
-    X.nonempty = reinterpret_cast<uint32_t *>(base + o_nonempty);
-    X.maps = base + o_maps;
+    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
     X.mbase = reinterpret_cast<uint64_t *>(base + o_mbase);
 
     // optimistic result capacity: what this pattern produced last time plus slack

@@ -8,10 +8,8 @@ bool mmg_filter_supported(int W, int lag_bytes);
 cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *blocks_per_sm);
 cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
                               cudaStream_t stream);
-cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
-cudaError_t mmg_launch_phases_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
-cudaError_t mmg_launch_scan_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
-                                 uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
+cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                               uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
 cudaError_t mmg_launch_scan(const uint32_t *counts, uint32_t n, uint64_t *bsum, uint64_t *bases, uint64_t *total,
                             cudaStream_t stream);
 cudaError_t mmg_launch_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,

@@ -215,7 +215,7 @@ __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState 
         if (lane == 0) {
             X.sub_start[st.open_t] = st.open_start;
             X.sub_count[st.open_t] = st.cursor - st.open_start;
-            X.nonempty[atomicAdd(X.n_nonempty, 1u)] = st.open_t;
+            X.hasev[st.open_t] = 1;
         }
         st.open_start = st.cursor;
     }
@@ -478,7 +478,13 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
 __device__ __forceinline__ bool events_overflowed(const MmgScratch &X) { return X.status[0] > X.ev_per_warp; }
 
 // ------------------------------------------------------------------------------------------
-// K1b: per sub-tile phase maps
+// K2: resolve -- everything after the filter in ONE kernel, one warp per engine block
+//   (a) lane per sub-tile with events: map entry phase -> exit phase for each alignment class
+//   (b) the maps are composed along the block's chains (sequentially over the few sub-tiles that
+//       have events, closed form for the event-free stretches in between)
+//   (c) lane per sub-tile: replay the TRUE chains through the events, mark visited matches
+//   (d) decoupled look-back over blocks (ticket order) gives the block's base in the output
+//   (e) ordered emission of (file offset, table base values)
 // ------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint32_t J0) {
@@ -487,90 +493,185 @@ __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint
     return x - n;
 }
 
-// one thread per sub-tile that owns events (grid-stride over the non-empty list)
-__global__ void __launch_bounds__(128)
-k_maps(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
-    if (events_overflowed(X)) return;
-    const uint32_t total = *X.n_nonempty;
-    const uint32_t W = P.W, npads = G.npads;
-    const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
-    uint32_t x[MMG_MAXL];
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const uint32_t t = X.nonempty[idx];
+#define LB_AGG (1ull << 62)
+#define LB_INCL (2ull << 62)
+#define LB_MASK ((1ull << 62) - 1)
+
+template <int W, bool BE>
+__device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t t,
+                                             uint64_t at, uint64_t *out_off, uint32_t *out_val) {
     const uint32_t n = X.sub_count[t];
     const uint32_t *ev = X.ev + X.sub_start[t];
-    for (uint32_t c = 0; c < npads; c++) {
-        for (uint32_t e = 0; e < Jmax; e++) x[e] = e;
-        bool any = false;
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t w = ev[i], off = MMG_EV_OFF(w);
-            if (W == 2 && (off & 1u) != c) continue;
-            const uint32_t q = off / W, j = MMG_EV_JUMP(w);
-            any = true;
-            for (uint32_t e = 0; e < Jmax; e++) {
-                const uint32_t xe = x[e];
-                if (xe <= q && (J0 == 1 || (q - xe) % J0 == 0)) x[e] = q + j;
-            }
-        }
-        if (any) {
-            X.hasmap[t * npads + c] = 1;                   // hasmap / mcount were zeroed by the host
-            X.chain_has[(t / G.spb) * npads + c] = 1;      // benign race: every writer stores 1
-            uint8_t *m = X.maps + (size_t)(t * npads + c) * X.jp;
-            for (uint32_t e = 0; e < Jmax; e++) m[e] = (uint8_t)lattice_advance(x[e], NP, J0);
-        }
-    }
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t w = ev[i];
+        if (!(w & MMG_EV_VISITED)) continue;
+        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
+        out_off[at] = (G.base_offset + s) >> G.report_shift;
+        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
+        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
+        out_val[at] = v0 | (v1 << 16);
+        at++;
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K2+K3: one warp per (block, alignment) chain composes the sub-tile maps (the entry phase of
-// every sub-tile that has events) and replays the TRUE chain through those sub-tiles' events,
-// marking the matches it visits.  Chains without events exit after one load.
-// ------------------------------------------------------------------------------------------
+#define RESOLVE_THREADS 128
 
-__global__ void __launch_bounds__(128)
-k_phases_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+template <int W, bool BE>
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
+          uint64_t *out_off, uint32_t *out_val, uint64_t capacity, uint32_t jp) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    // shared: maps [128][npads][jp] | entry phases [128][2] | has flags [128][2] | scalars
     const uint32_t npads = G.npads;
-    if (chain >= G.nblocks * npads || events_overflowed(X)) return;
-    if (!X.chain_has[chain]) return;
-    const uint32_t bi = chain / npads, c = chain % npads;
+    uint8_t *s_map = rs_smem;
+    uint8_t *s_ph = s_map + (size_t)RESOLVE_THREADS * npads * jp;
+    uint8_t *s_has = s_ph + RESOLVE_THREADS * 2;
+    __shared__ uint32_t s_bi, s_cnt[RESOLVE_THREADS / 32], s_phase[2];
+    __shared__ uint64_t s_before;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
+    if (tid == 0) { s_bi = atomicAdd(X.ticket, 1u); s_phase[0] = 0; s_phase[1] = 0; }
+    __syncthreads();
+    const uint32_t bi = s_bi;
+    if (bi >= G.nblocks) return;
+    const bool bad = events_overflowed(X);
     const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
-    const uint32_t W = P.W, J0 = P.J0, NP = MMG_SUBTILE / W;
-    uint32_t ph = 0;   // every chain starts at the first element of its view
-    for (uint32_t tb = t_begin; tb < t_end; tb += 32) {
-        const uint32_t t = tb + lane;
-        const uint32_t hm = (t < t_end) ? X.hasmap[t * npads + c] : 0;
-        uint32_t mask = __ballot_sync(FULL, hm != 0);
-        const uint32_t nvalid = min(32u, t_end - tb);
-        if (mask == 0) { ph = lattice_advance(ph, nvalid * NP, J0); continue; }
-        uint32_t my_ph = 0, done = 0;
-        while (mask) {
-            const uint32_t l = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);     // event-free sub-tiles in between
-            if ((uint32_t)lane == l) my_ph = ph;
-            ph = X.maps[(size_t)((tb + l) * npads + c) * X.jp + ph];
-            done = l + 1;
+    const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
+    uint32_t total = 0;       // matches of this block (valid in every thread after the loop)
+
+    for (uint32_t tb = t_begin; tb < t_end && !bad; tb += RESOLVE_THREADS) {
+        const uint32_t t = tb + tid;
+        const bool he = t < t_end && X.hasev[t] != 0;
+        const uint32_t nvalid = min((uint32_t)RESOLVE_THREADS, t_end - tb);
+        if (!__syncthreads_or(he)) {
+            if (tid == 0)
+                for (uint32_t c = 0; c < npads; c++) s_phase[c] = lattice_advance(s_phase[c], nvalid * NP, J0);
+            continue;
         }
-        if (nvalid > done) ph = lattice_advance(ph, (nvalid - done) * NP, J0);
-        if (hm) {
-            // replay this class's chain through the sub-tile's events
-            const uint32_t n = X.sub_count[t];
-            uint32_t *ev = X.ev + X.sub_start[t];
-            uint32_t x = my_ph, cnt = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t w = ev[i], off = MMG_EV_OFF(w);
-                if (W == 2 && (off & 1u) != c) continue;
-                const uint32_t q = off / W;
-                if (x <= q && (J0 == 1 || (q - x) % J0 == 0)) {
-                    if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
-                    x = q + MMG_EV_JUMP(w);
+        // (a) maps of this thread's sub-tile, both alignment classes
+        uint32_t n = 0;
+        uint32_t *ev = nullptr;
+        s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0;
+        if (he) {
+            n = X.sub_count[t];
+            ev = X.ev + X.sub_start[t];
+            for (uint32_t c = 0; c < npads; c++) {
+                uint32_t x[MMG_MAXL];
+                for (uint32_t e = 0; e < Jmax; e++) x[e] = e;
+                bool any = false;
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                    if (W == 2 && (off & 1u) != c) continue;
+                    const uint32_t q = off / W, j = MMG_EV_JUMP(w);
+                    any = true;
+                    for (uint32_t e = 0; e < Jmax; e++) {
+                        const uint32_t xe = x[e];
+                        if (xe <= q && (J0 == 1 || (q - xe) % J0 == 0)) x[e] = q + j;
+                    }
+                }
+                if (any) {
+                    s_has[tid * 2 + c] = 1;
+                    uint8_t *m = s_map + ((size_t)tid * npads + c) * jp;
+                    for (uint32_t e = 0; e < Jmax; e++) m[e] = (uint8_t)lattice_advance(x[e], NP, J0);
                 }
             }
-            if (cnt) atomicAdd(&X.mcount[t], cnt);
         }
+        __syncthreads();
+        // (b) phases: warp c composes the maps of class c over the sub-tiles of this round, in order
+        if (wid < (int)npads) {
+            const uint32_t c = wid;
+            uint32_t ph = s_phase[c], done = 0;
+            for (uint32_t g = 0; g < RESOLVE_THREADS && g < nvalid; g += 32) {
+                uint32_t m = __ballot_sync(FULL, g + lane < nvalid && s_has[(g + lane) * 2 + c]);
+                while (m) {
+                    const uint32_t l = g + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);
+                    if (lane == 0) s_ph[l * 2 + c] = (uint8_t)ph;
+                    ph = s_map[((size_t)l * npads + c) * jp + ph];
+                    done = l + 1;
+                }
+            }
+            if (nvalid > done) ph = lattice_advance(ph, (nvalid - done) * NP, J0);
+            if (lane == 0) s_phase[c] = ph;
+        }
+        __syncthreads();
+        // (c) replay the true chains through this thread's events
+        uint32_t cnt = 0;
+        if (he) {
+            uint32_t xc[2] = {s_has[tid * 2] ? s_ph[tid * 2] : 0u, s_has[tid * 2 + 1] ? s_ph[tid * 2 + 1] : 0u};
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                const uint32_t c = (W == 2) ? (off & 1u) : 0u;
+                const uint32_t q = off / W, x = xc[c];
+                if (x <= q && (J0 == 1 || (q - x) % J0 == 0)) {
+                    if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
+                    xc[c] = q + MMG_EV_JUMP(w);
+                }
+            }
+            X.mcount[t] = cnt;
+        }
+        const uint32_t wsum = __reduce_add_sync(FULL, cnt);
+        if (lane == 0) s_cnt[wid] = wsum;
+        __syncthreads();
+        for (int i = 0; i < RESOLVE_THREADS / 32; i++) total += s_cnt[i];
+        __syncthreads();
+    }
+
+    // (d) base of this block in the output: decoupled look-back, 32 predecessors per step
+    if (wid == 0) {
+        volatile uint64_t *lb = X.lookback;
+        uint64_t before = 0;
+        if (bi > 0) {
+            if (lane == 0) lb[bi] = LB_AGG | total;
+            int64_t hi = (int64_t)bi - 1;             // nearest predecessor not yet accounted for
+            for (;;) {
+                const int64_t j = hi - lane;
+                const uint64_t v = j >= 0 ? lb[j] : LB_INCL;          // "block -1" has an inclusive prefix of 0
+                const uint32_t flag = (uint32_t)(v >> 62);
+                const uint32_t incl = __ballot_sync(FULL, flag == 2);
+                const uint32_t stop = incl ? (uint32_t)__ffs(incl) - 1 : 32u;      // nearest inclusive prefix
+                const uint32_t need = stop == 32 ? FULL : ((2u << stop) - 1u);     // lanes 0..stop
+                if (__ballot_sync(FULL, flag == 0) & need) continue;               // somebody has not published yet
+                uint64_t part = (lane <= (int)stop) ? (v & LB_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                before += part;
+                if (stop < 32) break;
+                hi -= 32;
+            }
+        }
+        if (lane == 0) {
+            lb[bi] = LB_INCL | (before + total);
+            s_before = before;
+            if (bi == G.nblocks - 1) X.status[2] = before + total;
+        }
+    }
+    __syncthreads();
+    if (total == 0) return;
+
+    // (e) ordered emission
+    uint64_t running = s_before;
+    for (uint32_t tb = t_begin; tb < t_end; tb += RESOLVE_THREADS) {
+        const uint32_t t = tb + tid;
+        const bool he = t < t_end && X.hasev[t] != 0;
+        const uint32_t cnt = he ? X.mcount[t] : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();
+        if (lane == 31) s_cnt[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, round_total = 0;
+        for (int i = 0; i < RESOLVE_THREADS / 32; i++) { if (i < wid) wbase += s_cnt[i]; round_total += s_cnt[i]; }
+        const uint64_t at = running + wbase + (incl - cnt);
+        if (he) X.mbase[t] = at;
+        if (cnt && at + cnt <= capacity) emit_subtile<W, BE>(P, G, X, t, at, out_off, out_val);
+        running += round_total;
     }
 }
 
@@ -634,7 +735,7 @@ __global__ void __launch_bounds__(256) k_scan_final(const uint32_t *in, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: ordered emission
+// re-emission with an exactly sized buffer (only when the optimistic capacity of k_resolve was too small)
 // ------------------------------------------------------------------------------------------
 
 template <int W, bool BE>
@@ -642,85 +743,9 @@ __global__ void __launch_bounds__(128)
 k_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
        uint64_t *out_off, uint32_t *out_val) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G.nsub) return;
-    const uint32_t m = X.mcount[t];
-    if (m == 0) return;
-    uint64_t at = X.mbase[t];
-    const uint32_t n = X.sub_count[t];
-    const uint32_t *ev = X.ev + X.sub_start[t];
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t w = ev[i];
-        if (!(w & MMG_EV_VISITED)) continue;
-        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
-        out_off[at] = (G.base_offset + s) >> G.report_shift;
-        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
-        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
-        out_val[at] = v0 | (v1 << 16);
-        at++;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4+K5 fused: single-pass exclusive scan of the per-sub-tile match counts (decoupled look-back,
-// tiles drawn from a ticket counter so that every predecessor is already running) and ordered
-// emission into a buffer of `capacity` entries.  The host re-emits with k_emit when the
-// optimistic capacity was too small.
-// ------------------------------------------------------------------------------------------
-
-#define LB_AGG (1ull << 62)
-#define LB_INCL (2ull << 62)
-#define LB_MASK ((1ull << 62) - 1)
-
-template <int W, bool BE>
-__global__ void __launch_bounds__(256)
-k_scan_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
-            uint64_t *out_off, uint32_t *out_val, uint64_t capacity) {
-    __shared__ uint64_t ws[8];
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(X.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t t = tile * 256 + threadIdx.x;
-    const bool bad = events_overflowed(X);
-    const uint32_t m = (t < G.nsub && !bad) ? X.mcount[t] : 0u;
-    uint64_t tot;
-    const uint64_t excl = block_exclusive_scan(m, ws, &tot);
-    if (threadIdx.x == 0) {
-        volatile uint64_t *lb = X.lookback;
-        uint64_t before = 0;
-        if (tile > 0) {
-            lb[tile] = LB_AGG | tot;
-            int64_t j = (int64_t)tile - 1;
-            for (;;) {
-                const uint64_t v = lb[j];
-                if ((v >> 62) == 0) continue;                 // predecessor has not published yet
-                before += v & LB_MASK;
-                if ((v >> 62) == 2) break;
-                j--;
-            }
-        }
-        lb[tile] = LB_INCL | (before + tot);
-        s_prefix = before;
-        if (tile == gridDim.x - 1) X.status[2] = before + tot;
-    }
-    __syncthreads();
-    if (t >= G.nsub) return;
-    uint64_t at = s_prefix + excl;
-    X.mbase[t] = at;
-    if (m == 0 || at + m > capacity) return;
-    const uint32_t n = X.sub_count[t];
-    const uint32_t *ev = X.ev + X.sub_start[t];
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t w = ev[i];
-        if (!(w & MMG_EV_VISITED)) continue;
-        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
-        out_off[at] = (G.base_offset + s) >> G.report_shift;
-        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
-        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
-        out_val[at] = v0 | (v1 << 16);
-        at++;
-    }
+    if (t >= G.nsub || !X.hasev[t]) return;
+    if (X.mcount[t] == 0) return;
+    emit_subtile<W, BE>(P, G, X, t, X.mbase[t], out_off, out_val);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -873,24 +898,14 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
     return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, MMG_FILTER_WARPS * MMG_WARP_SMEM, stream);
 }
 
-cudaError_t mmg_launch_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
-    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)G.nsub + 127) / 128, 148ull * 8);
-    k_maps<<<grid, 128, 0, stream>>>(P, G, X);
-    return cudaGetLastError();
-}
-
-cudaError_t mmg_launch_phases_walk(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
-    const uint64_t chains = (uint64_t)G.nblocks * G.npads;
-    k_phases_walk<<<(unsigned)((chains * 32 + 127) / 128), 128, 0, stream>>>(P, G, X);
-    return cudaGetLastError();
-}
-
-cudaError_t mmg_launch_scan_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
-                                 uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
-    const unsigned grid = (G.nsub + 255) / 256;
-    if (P.W == 1) k_scan_emit<1, false><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
-    else if (G.big_endian) k_scan_emit<2, true><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
-    else k_scan_emit<2, false><<<grid, 256, 0, stream>>>(P, G, X, out_off, out_val, capacity);
+cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                               uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    const unsigned grid = G.nblocks;                 // one CTA per engine block
+    const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+    const size_t smem = (size_t)RESOLVE_THREADS * G.npads * jp + RESOLVE_THREADS * 4;
+    if (P.W == 1) k_resolve<1, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else if (G.big_endian) k_resolve<2, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else k_resolve<2, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     return cudaGetLastError();
 }
 

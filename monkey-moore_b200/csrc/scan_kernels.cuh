@@ -9,12 +9,11 @@
 //                   stream SWAR-style and flags the few windows whose first comparison does
 //                   not end in the default advance J0.  Flagged windows are evaluated exactly
 //                   and become EVENTS (window start, advance, match bit), grouped per sub-tile.
-//   K1b maps        per sub-tile and alignment class: the map  entry phase -> exit phase  of the
-//                   chain through the sub-tile's events (everything else advances by J0).
-//   K2+K3 phases/walk  one warp per (block, alignment) chain composes the maps and replays the TRUE
-//                   chain through each sub-tile's events, marking the matches it visits.
-//   K4+K5 scan/emit single-pass prefix sum of the per-sub-tile match counts fused with the ordered
-//                   emission of file offsets + table base values.
+//   K2  resolve     one warp per engine block: per sub-tile and alignment class the map  entry phase ->
+//                   exit phase  of the chain through the sub-tile's events (everything else advances by
+//                   J0); composition of the maps along the block's chains; replay of the TRUE chains
+//                   through the events (marks the matches they visit); decoupled look-back over the
+//                   per-block match counts; ordered emission of file offsets + table base values.
 //
 // Irregular geometries (block size not a multiple of the sub-tile) use the per-chain kernels G*.
 #ifndef MMG_SCAN_KERNELS_CUH
@@ -55,19 +54,15 @@ struct MmgGeom {
 struct MmgScratch {
     uint32_t *ev;          // event words, one private region per filter warp
     uint32_t ev_per_warp;
-    uint32_t *sub_start;   // [nsub] first event of the sub-tile (valid where the sub-tile owns events)
+    uint8_t *hasev;        // [nsub] sub-tile owns events (zeroed by the host, set by the filter)
+    uint32_t *sub_start;   // [nsub] first event of the sub-tile (valid where hasev)
     uint32_t *sub_count;   // [nsub] ditto
-    uint8_t *hasmap;       // [nsub*npads] (zeroed by the host)
-    uint8_t *maps;         // [nsub*npads*jp]
-    uint8_t *chain_has;    // [nblocks*npads] chain has at least one event (zeroed by the host)
-    uint32_t *mcount;      // [nsub] visited matches (zeroed by the host)
-    uint64_t *mbase;       // [nsub] exclusive prefix of mcount
-    uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events [2] total matches [3] next chunk (dynamic scheduling)
-    uint64_t *lookback;    // [ceil(nsub/256)] decoupled look-back words of the match-count scan (zeroed by the host)
-    uint32_t *ticket;      // tile ticket of the scan (zeroed by the host)
-    uint32_t *n_nonempty;  // number of sub-tiles that own events (zeroed by the host)
-    uint32_t *nonempty;    // [nsub] their indices, in completion order
-    uint32_t jp;           // bytes per map (Jmax rounded up to 16)
+    uint32_t *mcount;      // [nsub] visited matches (valid where hasev)
+    uint64_t *mbase;       // [nsub] position of the sub-tile's first match in the output (valid where hasev)
+    uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events
+                           // [2] total matches [3] next chunk (dynamic scheduling)   (zeroed by the host)
+    uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts (zeroed by the host)
+    uint32_t *ticket;      // block ticket of the resolve kernel (zeroed by the host)
 };
 
 #endif
