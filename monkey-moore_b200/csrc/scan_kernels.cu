@@ -45,17 +45,6 @@ __device__ __noinline__ uint32_t eval_window(const MmgProgram &P, const uint8_t 
     return 0x100u | (uint32_t)P.match_jump;
 }
 
-// number of elements of the (block, pad) view and whether window start `rel` (bytes from the
-// block start) begins a complete window   (src/core/search_engine.cpp:136-141)
-__device__ __forceinline__ bool window_in_block(const MmgProgram &P, uint32_t npads, uint64_t blk_size, uint64_t rel) {
-    const uint32_t W = P.W;
-    const uint32_t pad = (uint32_t)(rel % W);
-    if (pad >= npads) return false;
-    uint64_t count = blk_size / W;
-    if (pad + count * W > blk_size) count -= 1;
-    return rel / W + (uint64_t)P.L <= count;
-}
-
 // ------------------------------------------------------------------------------------------
 // K1: streaming filter
 // ------------------------------------------------------------------------------------------
@@ -223,27 +212,94 @@ __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState 
     return st;
 }
 
-// per-chunk constants of the exact-evaluation path
+// The filter kernel keeps the part of the pattern program that exact evaluation needs in shared memory
+// (file-scope __shared__: every device function reaches it with plain LDS instead of generic loads from
+// the kernel-parameter space).
+struct SProg {
+    int32_t ncheck, ntab, tab_default, match_jump, J0, modular;
+    int16_t ci[MMG_MAXL], clag[MMG_MAXL];
+    int32_t ced[MMG_MAXL], ccap[MMG_MAXL];
+    int32_t tkey[MMG_MAXL], tval[MMG_MAXL];
+    uint8_t tab8[512];      // 8-bit searches: skip for every possible difference d, indexed d + 255
+};
+__shared__ SProg g_sprog;
+
+__device__ __forceinline__ void load_sprog(const MmgProgram &P) {
+    if (threadIdx.x == 0) {
+        g_sprog.ncheck = P.ncheck; g_sprog.ntab = P.ntab; g_sprog.tab_default = P.tab_default;
+        g_sprog.match_jump = P.match_jump; g_sprog.J0 = P.J0; g_sprog.modular = P.modular;
+    }
+    for (int i = threadIdx.x; i < P.ncheck; i += blockDim.x) {
+        g_sprog.ci[i] = P.chk[i].i; g_sprog.clag[i] = P.chk[i].lag; g_sprog.ced[i] = P.chk[i].ed; g_sprog.ccap[i] = P.chk[i].cap;
+    }
+    for (int i = threadIdx.x; i < P.ntab; i += blockDim.x) { g_sprog.tkey[i] = P.tab_key[i]; g_sprog.tval[i] = P.tab_val[i]; }
+    if (P.W == 1) {
+        for (int i = threadIdx.x; i < 511; i += blockDim.x) {
+            int sk = P.tab_default;
+            for (int j = 0; j < P.ntab; j++)
+                if (P.tab_key[j] == i - 255) sk = P.tab_val[j];
+            g_sprog.tab8[i] = (uint8_t)sk;
+        }
+    }
+    __syncthreads();
+}
+
+// F(s) from the shared-memory program: advance in bits [7:0], 0x100 when the window matches.
+template <int W, bool BE>
+__device__ __forceinline__ uint32_t eval_window_s(const uint8_t *w) {
+    const uint32_t vmask = W == 1 ? 0xFFu : 0xFFFFu;
+    const int nc = g_sprog.ncheck;
+    for (int c = 0; c < nc; c++) {
+        const int i = g_sprog.ci[c];
+        const int cur = (int)ld_elem<W, BE>(w + i * W);
+        const int prv = (int)ld_elem<W, BE>(w + (i - g_sprog.clag[c]) * W);
+        const int d = cur - prv;
+        const int ed = g_sprog.ced[c];
+        const bool pass = g_sprog.modular ? ((((uint32_t)(d - ed)) & vmask) == 0) : (d == ed);
+        if (!pass) {
+            int sk;
+            if (W == 1) {
+                sk = g_sprog.tab8[d + 255];
+            } else {
+                sk = g_sprog.tab_default;
+                const int nt = g_sprog.ntab;
+#pragma unroll 1
+                for (int j = 0; j < nt; j++)
+                    if (g_sprog.tkey[j] == d) sk = g_sprog.tval[j];
+            }
+            return (uint32_t)min(g_sprog.ccap[c], sk);
+        }
+    }
+    return 0x100u | (uint32_t)g_sprog.match_jump;
+}
+
+// per-chunk constants of the exact-evaluation path (kept in registers / local memory of the warp)
 struct ChunkCtx {
     int64_t s_lo, s_hi;      // window starts owned by this chunk
     int64_t q_base;          // queue entries are (window start - q_base)
-    uint64_t blk_off, blk_size;
+    int64_t blk_off;
+    int64_t max_rel[2];      // last byte offset (from the block start) that begins a complete window, per alignment; -1: none
+    const uint8_t *data;
+    uint32_t *ev;
     uint32_t reg_hi;
+    uint32_t npads;
 };
 
 // Exact evaluation of up to 32 queued candidate windows (one per lane, ascending window start)
 // and ordered append of the resulting events to the warp's private event region.
 template <int W, bool BE>
-__device__ __noinline__ WarpState eval_batch(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, WarpState st,
-                                             const ChunkCtx &C, uint32_t entry, bool have, int lane) {
+__device__ __noinline__ WarpState eval_batch(const MmgScratch &X, WarpState st, const ChunkCtx &C, uint32_t entry, bool have,
+                                             int lane) {
     bool is_event = false;
     uint32_t word = 0, ts = 0;
     if (have) {
         const int64_t s = C.q_base + (int64_t)entry;
-        if (s >= C.s_lo && s < C.s_hi && window_in_block(P, G.npads, C.blk_size, (uint64_t)s - C.blk_off)) {
-            const uint32_t r = eval_window<W, BE>(P, G.data + s);
+        const int64_t rel = s - C.blk_off;
+        const uint32_t pad = (uint32_t)rel & (uint32_t)(W - 1);
+        if (s >= C.s_lo && s < C.s_hi && pad < C.npads && rel <= C.max_rel[pad]) {
+            const uint32_t r = eval_window_s<W, BE>(C.data + s);
             const uint32_t jump = r & 0xFFu;
-            if ((r & 0x100u) || jump != (uint32_t)P.J0) {     // default advance without a match is not an event
+            if ((r & 0x100u) || jump != (uint32_t)g_sprog.J0) {     // default advance without a match is not an event
                 is_event = true;
                 ts = (uint32_t)((uint64_t)s >> MMG_SUBTILE_SHIFT);
                 word = ((uint32_t)s & (MMG_SUBTILE - 1)) | (jump << 16) | ((r & 0x100u) ? MMG_EV_MATCH : 0u);
@@ -258,7 +314,7 @@ __device__ __noinline__ WarpState eval_batch(const MmgProgram &P, const MmgGeom 
         st = close_until(X, st, tt, lane);
         if (is_event && ts == tt) {
             const uint32_t at = st.cursor + __popc(grp & lt);
-            if (at < C.reg_hi) X.ev[at] = word;
+            if (at < C.reg_hi) C.ev[at] = word;
         }
         st.cursor += __popc(grp);
         pending &= ~grp;
@@ -350,7 +406,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncwarp();
+    load_sprog(P);      // includes the only __syncthreads() of the kernel
 
     WarpState st;
     st.cursor = reg_lo;
@@ -367,8 +423,19 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         const uint32_t t1 = min(t0 + G.chunk_subs, G.nsub);
         const uint32_t bi = t0 / G.spb;
         ChunkCtx C;
-        C.blk_off = (uint64_t)bi * G.B;
-        C.blk_size = min(G.B + (uint64_t)G.ov, G.S - C.blk_off);
+        C.blk_off = (int64_t)((uint64_t)bi * G.B);
+        {
+            // element count of each alignment's view of the block (src/core/search_engine.cpp:136-141)
+            const uint64_t blk_size = min(G.B + (uint64_t)G.ov, G.S - (uint64_t)C.blk_off);
+            for (uint32_t pad = 0; pad < 2; pad++) {
+                uint64_t count = blk_size / W;
+                if (pad + count * W > blk_size) count -= 1;
+                C.max_rel[pad] = (pad < G.npads && count >= (uint64_t)P.L) ? (int64_t)(pad + (count - (uint64_t)P.L) * W) : -1;
+            }
+        }
+        C.data = G.data;
+        C.ev = X.ev;
+        C.npads = G.npads;
         C.s_lo = (int64_t)t0 << MMG_SUBTILE_SHIFT;
         C.s_hi = (int64_t)t1 << MMG_SUBTILE_SHIFT;
         C.reg_hi = reg_lo + X.ev_per_warp;
@@ -426,26 +493,30 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                     // exact per-position flags (16-bit: only now), then ordered enqueue of the candidates
                     if (LB != 0 && W == 2) any = any && filter_lane<2, LB, BE, 0>(P, x, f);
                     const uint32_t cm = candidate_mask<W, LB>(f, any);
-                    const int cnt = __popc(cm);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += v;
+                    // exclusive prefix of the per-lane counts (<= 16) from bit-sliced ballots
+                    const uint32_t cnt = __popc(cm);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const uint32_t b0 = __ballot_sync(FULL, cnt & 1u), b1 = __ballot_sync(FULL, cnt & 2u);
+                    uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
+                    uint32_t total = __popc(b0) + 2u * __popc(b1);
+                    if (__any_sync(FULL, cnt >= 4u)) {
+                        const uint32_t b2 = __ballot_sync(FULL, cnt & 4u), b3 = __ballot_sync(FULL, cnt & 8u),
+                                       b4 = __ballot_sync(FULL, cnt & 16u);
+                        pre += 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt) + 16u * __popc(b4 & lt);
+                        total += 4u * __popc(b2) + 8u * __popc(b3) + 16u * __popc(b4);
                     }
-                    const int total = __shfl_sync(FULL, incl, 31);
-                    uint32_t at = qn + (uint32_t)(incl - cnt);
+                    uint32_t at = qn + pre;
                     const uint32_t rel = rel_stage + r * MMG_ROW + (uint32_t)lane * 16u;   // candidate bit 0 of this lane
                     uint32_t m = cm;
                     while (m) {
                         queue[at++] = rel + (uint32_t)(__ffs(m) - 1);
                         m &= m - 1;
                     }
-                    qn += (uint32_t)total;
+                    qn += total;
                     __syncwarp();
                     uint32_t qh = 0;
                     while (qn - qh >= 32) {
-                        st = eval_batch<W, BE>(P, G, X, st, C, queue[qh + lane], true, lane);
+                        st = eval_batch<W, BE>(X, st, C, queue[qh + lane], true, lane);
                         qh += 32;
                     }
                     if (qh) {          // move the < 32 left-overs to the front
@@ -464,7 +535,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                             ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
             if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
         }
-        if (qn) st = eval_batch<W, BE>(P, G, X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+        if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
         __syncwarp();
         st = close_until(X, st, t1, lane);
     }
@@ -840,16 +911,21 @@ cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint
 
 #include "launch.h"
 
-// NK (compile-time key count) per width: 8-bit unrolls up to 4 keys, 16-bit fuses the single-key case.
+// NK (compile-time key count) per width: 8-bit unrolls up to 8 keys, 16-bit fuses the single-key case.
 template <int W, int LB, bool BE>
 static const void *filter_for_keys(int nkeys) {
     if (LB == 0) return (const void *)k_filter<W, LB, BE, 0>;
     if (W == 1) {
+        if (LB > 4) return (const void *)k_filter<W, LB, BE, 0>;      // long wildcard gaps: run-time key loop only
         switch (nkeys) {
-            case 1: return (const void *)k_filter<W, LB, BE, 1>;
-            case 2: return (const void *)k_filter<W, LB, BE, 2>;
-            case 3: return (const void *)k_filter<W, LB, BE, 3>;
-            case 4: return (const void *)k_filter<W, LB, BE, 4>;
+            case 1: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 1>;
+            case 2: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 2>;
+            case 3: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 3>;
+            case 4: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 4>;
+            case 5: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 5>;
+            case 6: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 6>;
+            case 7: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 7>;
+            case 8: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 8>;
             default: return (const void *)k_filter<W, LB, BE, 0>;
         }
     }
