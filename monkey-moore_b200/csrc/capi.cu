@@ -119,7 +119,7 @@ struct mmg_results {
     ScanRequest rq{};
     TiledState t;
     Arena *arena = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after H2D, after filter, end
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, after H2D, after filter, end, before filter
     uint64_t *status_host = nullptr;                            // pinned slot receiving X.status
     uint32_t launches = 0;
 };
@@ -204,6 +204,7 @@ void enqueue_tiled(mmg_results *res, bool record_filter_event) {
     t.X.ev_per_warp = (uint32_t)t.per_warp;
     t.X.ev = res->arena->get<uint32_t>(t.per_warp * t.total_warps);
     CU(cudaMemsetAsync(t.base, 0, t.zero_bytes, stream));
+    if (record_filter_event) CU(cudaEventRecord(res->ev[4], stream));
     CU(mmg_launch_filter(P, t.G, t.X, t.lag_bytes, t.grid, stream));
     if (record_filter_event) CU(cudaEventRecord(res->ev[2], stream));
     CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
@@ -321,7 +322,7 @@ int finish_scan(mmg_results *r) {
         else CU(cudaEventSynchronize(r->ev[3]));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1])); r->stats.ms_h2d = r->from_host ? ms : 0.f;
-        CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
+        CU(cudaEventElapsedTime(&ms, r->tiled ? r->ev[4] : r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
         CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[3])); r->stats.ms_total = ms;
         r->stats.launches = r->launches;
     } catch (const ScanError &e) {

@@ -560,8 +560,10 @@ __device__ __forceinline__ bool events_overflowed(const MmgScratch &X) { return 
 
 __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint32_t J0) {
     // first chain position >= n when the chain sits at x and advances by J0; returned relative to n
-    if (x < n) x += ((n - x + J0 - 1) / J0) * J0;
-    return x - n;
+    if (x >= n) return x - n;
+    if (J0 == 1) return 0;
+    const uint32_t r = (n - x) % J0;
+    return r ? J0 - r : 0;
 }
 
 #define LB_AGG (1ull << 62)
@@ -690,27 +692,36 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         __syncthreads();
     }
 
-    // (d) base of this block in the output: decoupled look-back, 32 predecessors per step
+    // (d) base of this block in the output: decoupled look-back, 8 x 32 predecessors per step (the eight
+    // window loads are independent, so a block far from the nearest inclusive prefix still needs few round trips)
     if (wid == 0) {
         volatile uint64_t *lb = X.lookback;
         uint64_t before = 0;
         if (bi > 0) {
             if (lane == 0) lb[bi] = LB_AGG | total;
             int64_t hi = (int64_t)bi - 1;             // nearest predecessor not yet accounted for
-            for (;;) {
-                const int64_t j = hi - lane;
-                const uint64_t v = j >= 0 ? lb[j] : LB_INCL;          // "block -1" has an inclusive prefix of 0
-                const uint32_t flag = (uint32_t)(v >> 62);
-                const uint32_t incl = __ballot_sync(FULL, flag == 2);
-                const uint32_t stop = incl ? (uint32_t)__ffs(incl) - 1 : 32u;      // nearest inclusive prefix
-                const uint32_t need = stop == 32 ? FULL : ((2u << stop) - 1u);     // lanes 0..stop
-                if (__ballot_sync(FULL, flag == 0) & need) continue;               // somebody has not published yet
-                uint64_t part = (lane <= (int)stop) ? (v & LB_MASK) : 0ull;
+            bool finished = false;
+            while (!finished) {
+                uint64_t v[8];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-                before += part;
-                if (stop < 32) break;
-                hi -= 32;
+                for (int k = 0; k < 8; k++) {
+                    const int64_t j = hi - 32 * k - lane;
+                    v[k] = j >= 0 ? lb[j] : LB_INCL;                  // "block -1" has an inclusive prefix of 0
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t flag = (uint32_t)(v[k] >> 62);
+                    const uint32_t incl = __ballot_sync(FULL, flag == 2);
+                    const uint32_t stop = incl ? (uint32_t)__ffs(incl) - 1 : 32u;      // nearest inclusive prefix
+                    const uint32_t need = stop == 32 ? FULL : ((2u << stop) - 1u);     // lanes 0..stop
+                    if (__ballot_sync(FULL, flag == 0) & need) break;                  // not published yet: reload from hi
+                    uint64_t part = (lane <= (int)stop) ? (v[k] & LB_MASK) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                    before += part;
+                    hi -= 32;
+                    if (stop < 32) { finished = true; break; }
+                }
             }
         }
         if (lane == 0) {
