@@ -193,6 +193,8 @@ def run_ours(args, w):
             return bytes(t.cpu().tolist())
         comm = mm.Comm(rank, world, bcast)     # the library's own NCCL communicator for the result gather
 
+    pending_gather = [None]
+
     def step(collect=None):
         launches, filt_ms, filt_bytes = 0, 0.0, 0
         # the searches of a step are independent: enqueue them all, then complete them (the host work of
@@ -206,13 +208,17 @@ def run_ours(args, w):
             filt_ms += st["ms_filter"]
             filt_bytes += st["bytes_scanned"] + 8 * res.count
         if world > 1:
-            gathered = comm.gather(held, fetch=collect is not None)   # ONE grouped NCCL op per step
+            # ONE grouped NCCL op per step, only enqueued here; rank 0 completes the previous step's gather
+            # (header read, possible spill receives) when its object is dropped below
+            gathered = comm.gather(held, lazy=True)
             if collect is not None and gathered is not None:
-                collect.extend(torch.from_numpy(g[0].astype(np.int64)) for g in gathered)
-        elif collect is not None:
-            collect.extend(r.torch_offsets() for r in held)
-        for r in held:
-            r.close()
+                collect.extend(torch.from_numpy(g[0].astype(np.int64)) for g in gathered.fetch())
+            pending_gather[0] = gathered        # dropping the previous one closes it (and its result lists)
+        else:
+            if collect is not None:
+                collect.extend(r.torch_offsets() for r in held)
+            for r in held:
+                r.close()
         return launches, filt_ms, filt_bytes
 
     def barrier():

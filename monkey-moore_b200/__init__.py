@@ -234,32 +234,55 @@ class Comm:
         _check(lib().mmg_comm_create(C.create_string_buffer(raw, 128), rank, world, int(capacity), C.byref(h)))
         self._h = h
 
-    def gather(self, results, fetch=False):
+    def gather(self, results, fetch=False, lazy=False):
+        """Collective.  ``lazy=True`` only enqueues the gather and returns a :class:`Gathered` (rank 0) that
+        completes on first use; otherwise rank 0 gets the per-search counts (or the lists with ``fetch=True``)."""
         n = len(results)
         arr = (C.c_void_p * n)(*[r._h for r in results])
         g = C.c_void_p()
         _check(lib().mmg_comm_gather(self._h, arr, n, C.byref(g)))
         if not g:
             return None
-        try:
-            counts = [int(lib().mmg_gathered_count(g, k)) for k in range(n)]
-            if not fetch:
-                return counts
-            out = []
-            for k in range(n):
-                off = np.zeros(counts[k], np.uint64)
-                val = np.zeros((counts[k], 2), np.uint32)
-                if counts[k]:
-                    _check(lib().mmg_gathered_copy(g, k, off.ctypes.data_as(_u64p), val.ctypes.data_as(_u32p)))
-                out.append((off, val))
+        out = Gathered(g, n, list(results))
+        if lazy:
             return out
+        try:
+            return out.fetch() if fetch else out.counts()
         finally:
-            lib().mmg_gathered_free(g)
+            out.close()
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.mmg_comm_destroy(self._h)
             self._h = None
+
+    __del__ = close
+
+
+class Gathered:
+    """Rank 0's view of one gather.  Keeps the rank's own result lists alive until the gather is complete."""
+
+    def __init__(self, handle, nlists, keep):
+        self._h, self.nlists, self._keep = handle, nlists, keep
+
+    def counts(self):
+        return [int(lib().mmg_gathered_count(self._h, k)) for k in range(self.nlists)]
+
+    def fetch(self):
+        out = []
+        for k, n in enumerate(self.counts()):
+            off = np.zeros(n, np.uint64)
+            val = np.zeros((n, 2), np.uint32)
+            if n:
+                _check(lib().mmg_gathered_copy(self._h, k, off.ctypes.data_as(_u64p), val.ctypes.data_as(_u32p)))
+            out.append((off, val))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mmg_gathered_free(self._h)
+            self._h = None
+            self._keep = None
 
     __del__ = close
 

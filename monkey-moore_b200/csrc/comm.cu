@@ -77,6 +77,8 @@ int err(int code, const std::string &msg) {
 
 }  // namespace
 
+struct mmg_gathered;
+
 struct mmg_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -85,18 +87,77 @@ struct mmg_comm {
     uint32_t *pack_val = nullptr;
     uint64_t *recv_off = nullptr;   // rank 0: world * cap
     uint32_t *recv_val = nullptr;
-    uint64_t *hdr_host = nullptr;   // pinned: this rank's header (send side), all headers (rank 0)
+    uint64_t *hdr_host = nullptr;   // pinned, rank 0: the headers of all ranks (64 entries per rank)
+    mmg_gathered *inflight = nullptr;   // rank 0: a gather whose headers have not been read yet
 };
 
 struct mmg_gathered {
     int nlists = 0;
     std::vector<uint64_t> counts;                 // per list: total over ranks
-    std::vector<std::vector<uint64_t>> offsets;   // host copies, assembled lazily? no: kept on device
     // device pieces per list in rank order: (pointer, n) pairs into recv buffers / spill buffers
     struct Piece { const uint64_t *off; const uint32_t *val; uint64_t n; };
     std::vector<std::vector<Piece>> pieces;
     std::vector<void *> owned;                    // spill buffers to free
+    // deferred completion (rank 0): headers are read and spills received on first use
+    bool pending = false;
+    mmg_comm *comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;                  // headers have landed in hdr_host
+    std::vector<mmg_results_view> own;            // rank 0's own lists (their overflow is copied on completion)
+    int error = MMG_OK;
 };
+
+namespace {
+
+// rank 0: read the gathered headers, build the piece lists, receive what did not fit into the packed buffers
+int finish_gather(mmg_gathered *g) {
+    if (!g->pending) return g->error;
+    g->pending = false;
+    mmg_comm *c = g->comm;
+    if (c->inflight == g) c->inflight = nullptr;
+    cudaStream_t stream = g->stream;
+    const int nlists = g->nlists;
+    const uint64_t room = c->cap - (uint64_t)nlists;
+    auto bail = [&](int code) { g->error = code; return code; };
+    if (cudaEventSynchronize(g->ready) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "waiting for the gathered headers failed"));
+    cudaEventDestroy(g->ready);
+    g->ready = nullptr;
+    const uint64_t *all = c->hdr_host;
+    bool spilled = false;
+    for (int r = 0; r < c->world; r++) {
+        uint64_t pos = nlists, used_r = 0;
+        for (int k = 0; k < nlists; k++) {
+            const uint64_t n = all[(size_t)r * 64 + k];
+            const uint64_t f = std::min<uint64_t>(n, room - used_r);
+            g->counts[k] += n;
+            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
+            pos += f; used_r += f;
+            if (f < n) {
+                const uint64_t rest = n - f;
+                uint64_t *so; uint32_t *sv;
+                if (cudaMalloc((void **)&so, rest * sizeof(uint64_t)) != cudaSuccess ||
+                    cudaMalloc((void **)&sv, rest * sizeof(uint32_t)) != cudaSuccess)
+                    return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
+                g->owned.push_back(so); g->owned.push_back(sv);
+                if (r == 0) {
+                    if (cudaMemcpyAsync(so, g->own[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+                        cudaMemcpyAsync(sv, g->own[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                        return bail(err(MMG_ERR_CUDA, "copying rank 0's overflow failed"));
+                } else {
+                    if (nccl().Recv(so, rest, ncclUint64, r, c->comm, stream) != ncclSuccess ||
+                        nccl().Recv(sv, rest, ncclUint32, r, c->comm, stream) != ncclSuccess)
+                        return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
+                }
+                g->pieces[k].push_back({so, sv, rest});
+                spilled = true;
+            }
+        }
+    }
+    if (spilled && cudaStreamSynchronize(stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "spill transfer failed"));
+    return MMG_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -123,13 +184,14 @@ int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, m
         CUC(cudaMalloc((void **)&c->recv_off, (size_t)world * c->cap * sizeof(uint64_t)));
         CUC(cudaMalloc((void **)&c->recv_val, (size_t)world * c->cap * sizeof(uint32_t)));
     }
-    CUC(cudaHostAlloc((void **)&c->hdr_host, (size_t)(world + 1) * 64 * sizeof(uint64_t), cudaHostAllocDefault));
+    CUC(cudaHostAlloc((void **)&c->hdr_host, (size_t)world * 64 * sizeof(uint64_t), cudaHostAllocDefault));
     *out = c;
     return MMG_OK;
 }
 
 void mmg_comm_destroy(mmg_comm *c) {
     if (!c) return;
+    if (c->inflight) finish_gather(c->inflight);
     if (c->comm) nccl().CommDestroy(c->comm);
     cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
     cudaFreeHost(c->hdr_host);
@@ -138,16 +200,20 @@ void mmg_comm_destroy(mmg_comm *c) {
 
 // Gathers `nlists` result lists (the searches of one step) of every rank to rank 0.
 // On rank 0 *out receives the gathered lists (rank order == ascending file offsets); elsewhere NULL.
+// The call only ENQUEUES work on the scan stream; rank 0 completes it (header read, spill receives) when
+// the gathered object is first used or freed.  If rank 0's own lists may overflow the packed buffer they
+// must stay alive until then.
 int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out) {
     if (!c || !lists || nlists <= 0 || nlists > 60 || !out) return err(MMG_ERR_ARG, "bad gather arguments");
     *out = nullptr;
+    if (c->inflight) finish_gather(c->inflight);          // its headers live in the buffer we are about to reuse
     cudaStream_t stream = static_cast<cudaStream_t>(mmg_internal_stream());
     const uint64_t room = c->cap - (uint64_t)nlists;
     std::vector<mmg_results_view> v(nlists);
     for (int k = 0; k < nlists; k++) mmg_internal_results_view(lists[k], &v[k]);
 
     // pack: header (counts) + as much of every list as fits
-    uint64_t *hdr = c->hdr_host;            // slot 0: my header
+    uint64_t hdr[64];
     uint64_t at = nlists, used = 0;
     std::vector<uint64_t> fit(nlists);
     for (int k = 0; k < nlists; k++) {
@@ -159,6 +225,7 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
         }
         at += fit[k]; used += fit[k];
     }
+    // pageable source: the runtime stages it before returning, so `hdr` may go out of scope
     CUC(cudaMemcpyAsync(c->pack_off, hdr, (size_t)nlists * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
 
     // one grouped NCCL operation moves every rank's packed buffers to rank 0
@@ -175,73 +242,48 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
     NC(nccl().GroupEnd());
 
     if (c->rank != 0) {
-        // what did not fit travels point-to-point; rank 0 posts the matching receives
+        // what did not fit travels point-to-point; rank 0 posts the matching receives when it completes the gather.
+        // Stream order keeps the lists alive: their cudaFreeAsync is queued behind these sends.
         for (int k = 0; k < nlists; k++) {
             if (fit[k] < v[k].count) {
                 NC(nccl().Send(v[k].d_off + fit[k], v[k].count - fit[k], ncclUint64, 0, c->comm, stream));
                 NC(nccl().Send(v[k].d_val + fit[k], v[k].count - fit[k], ncclUint32, 0, c->comm, stream));
             }
         }
-        CUC(cudaStreamSynchronize(stream));   // the lists may be freed by the caller right after
         return MMG_OK;
     }
 
-    // rank 0: own buffers + everybody's headers
+    // rank 0: own buffers + everybody's headers (read back asynchronously)
     CUC(cudaMemcpyAsync(c->recv_off, c->pack_off, c->cap * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
     CUC(cudaMemcpyAsync(c->recv_val, c->pack_val, c->cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-    uint64_t *all = c->hdr_host + 64;
-    CUC(cudaMemcpy2DAsync(all, 64 * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t), (size_t)nlists * sizeof(uint64_t),
-                          c->world, cudaMemcpyDeviceToHost, stream));
-    CUC(cudaStreamSynchronize(stream));
-
+    CUC(cudaMemcpy2DAsync(c->hdr_host, 64 * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t),
+                          (size_t)nlists * sizeof(uint64_t), c->world, cudaMemcpyDeviceToHost, stream));
     mmg_gathered *g = new mmg_gathered();
     g->nlists = nlists;
     g->counts.assign(nlists, 0);
     g->pieces.resize(nlists);
-    for (int r = 0; r < c->world; r++) {
-        uint64_t pos = nlists, used_r = 0;
-        for (int k = 0; k < nlists; k++) {
-            const uint64_t n = all[(size_t)r * 64 + k];
-            const uint64_t f = std::min<uint64_t>(n, room - used_r);
-            g->counts[k] += n;
-            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
-            pos += f; used_r += f;
-            if (f < n) {
-                const uint64_t rest = n - f;
-                if (r == 0) {
-                    // rank 0's own overflow stays where it is; copy so that the caller may free its lists
-                    uint64_t *so; uint32_t *sv;
-                    CUC(cudaMalloc((void **)&so, rest * sizeof(uint64_t)));
-                    CUC(cudaMalloc((void **)&sv, rest * sizeof(uint32_t)));
-                    g->owned.push_back(so); g->owned.push_back(sv);
-                    CUC(cudaMemcpyAsync(so, v[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
-                    CUC(cudaMemcpyAsync(sv, v[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-                    g->pieces[k].push_back({so, sv, rest});
-                } else {
-                    uint64_t *so; uint32_t *sv;
-                    CUC(cudaMalloc((void **)&so, rest * sizeof(uint64_t)));
-                    CUC(cudaMalloc((void **)&sv, rest * sizeof(uint32_t)));
-                    g->owned.push_back(so); g->owned.push_back(sv);
-                    NC(nccl().Recv(so, rest, ncclUint64, r, c->comm, stream));
-                    NC(nccl().Recv(sv, rest, ncclUint32, r, c->comm, stream));
-                    g->pieces[k].push_back({so, sv, rest});
-                }
-            }
-        }
-    }
-    CUC(cudaStreamSynchronize(stream));
+    g->pending = true;
+    g->comm = c;
+    g->stream = stream;
+    g->own = v;
+    CUC(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
+    CUC(cudaEventRecord(g->ready, stream));
+    c->inflight = g;
     *out = g;
     return MMG_OK;
 }
 
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list) {
-    return (g && list >= 0 && list < g->nlists) ? g->counts[list] : 0;
+    if (!g || list < 0 || list >= g->nlists) return 0;
+    finish_gather(const_cast<mmg_gathered *>(g));
+    return g->counts[list];
 }
 
 // Copies list `list` (all ranks, ascending file offsets) to host buffers: offsets[count], values[2*count].
 // Valid until the next mmg_comm_gather on the same communicator.
 int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32_t *values) {
     if (!g || list < 0 || list >= g->nlists) return err(MMG_ERR_ARG, "bad gathered list");
+    if (int rc = finish_gather(const_cast<mmg_gathered *>(g)); rc != MMG_OK) return rc;
     uint64_t at = 0;
     for (const auto &p : g->pieces[list]) {
         if (offsets) CUC(cudaMemcpy(offsets + at, p.off, p.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -257,6 +299,8 @@ int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32
 
 void mmg_gathered_free(mmg_gathered *g) {
     if (!g) return;
+    finish_gather(g);
+    if (g->ready) cudaEventDestroy(g->ready);
     for (void *p : g->owned) cudaFree(p);
     delete g;
 }
