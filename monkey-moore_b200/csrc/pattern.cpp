@@ -201,6 +201,19 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
         for (int j = 0; j < d.ntab; j++)
             if (std::min(cap0, d.tab_val[j]) != d.J0) add_key(d.tab_key[j]);
         d.nkeys = static_cast<int32_t>(keys.size());
+        // depth-2 refinement of the 8-bit filter: valid when comparisons 0 and 1 look at adjacent byte pairs with
+        // exact arithmetic, keys[0] is the pass key and no other key aliases it modulo 256 (scan_kernels.cu)
+        {
+            const int32_t ed0 = d.chk[0].ed;
+            bool ok = d.W == 1 && !d.modular && d.ncheck >= 2 && d.chk[0].lag == 1 && d.chk[1].lag == 1 &&
+                      d.chk[1].i == d.chk[0].i - 1 && ed0 <= vmax && ed0 >= -vmax && !keys.empty() &&
+                      keys[0] == (static_cast<uint32_t>(ed0) & vmask);
+            for (int j = 0; j < d.ntab && ok; j++)      // another key with the same residue would hide behind keys[0]
+                if (d.tab_key[j] != ed0 && ((static_cast<uint32_t>(d.tab_key[j]) ^ static_cast<uint32_t>(ed0)) & vmask) == 0 &&
+                    d.tab_key[j] <= vmax && d.tab_key[j] >= -vmax && std::min(cap0, d.tab_val[j]) != d.J0)
+                    ok = false;
+            d.d2ok = ok ? 1 : 0;
+        }
         for (size_t j = 0; j < keys.size(); j++) {
             d.keys[j] = d.W == 1 ? keys[j] * 0x01010101u : ((1u - keys[j]) & 0xFFFFu) * 0x00010001u;
             d.pkeys[j] = (((1u - keys[j]) & 0xFFFFu) << 16) | ((0u - keys[j]) & 0xFFFFu);

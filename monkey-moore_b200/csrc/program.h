@@ -37,6 +37,7 @@ struct MmgProgram {
     int32_t first_lit;    // keyword index whose element yields the table base value (v0)
     int32_t opp_idx;      // keyword index of the first opposite-case letter (v1), or -1
     int32_t nkeys;        // filter keys; -1 => every window must be evaluated exactly
+    int32_t d2ok;         // 8-bit filter may refine "comparison 0 passes" candidates with comparison 1 (see filter_lane)
     // Differences (mod 2^(8W)) of comparison 0 that do NOT lead to a J0 advance, stored as the
     // SWAR constant the filter kernel consumes:  W=1: k * 0x01010101 ;  W=2: ((1-k) & 0xFFFF) * 0x00010001
     uint32_t keys[MMG_MAXL + 1];

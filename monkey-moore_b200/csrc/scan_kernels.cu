@@ -8,6 +8,9 @@
 #include "scan_kernels.cuh"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #define FULL 0xFFFFFFFFu
 
@@ -68,45 +71,67 @@ __device__ __forceinline__ uint32_t extract(const uint32_t (&x)[8]) {
 //   W=2: f[c*4+k] has a zero 16-bit half h  <=> the element starting at byte 4k-c+2h is flagged
 // NK > 0: number of keys known at compile time (fully unrolled); NK == 0: P.nkeys at run time.
 template <int W, int LB, bool BE, int NK>
-__device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t (&x)[8], uint32_t (&f)[8]) {
+__device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t (&x)[8], uint32_t (&f)[8], bool depth2 = false) {
     if (LB == 0) return true;   // evaluate-everything mode
     const int nk = NK > 0 ? NK : P.nkeys;
     if (W == 1) {
-        uint32_t d[4];
-        d[0] = __vsub4(x[4], extract<16 - LB, false>(x));
-        d[1] = __vsub4(x[5], extract<20 - LB, false>(x));
-        d[2] = __vsub4(x[6], extract<24 - LB, false>(x));
-        d[3] = __vsub4(x[7], extract<28 - LB, false>(x));
-        {   // first key peeled: no accumulator initialisation
+        // d[1..4]: byte-wise differences of this lane's four words; d[0]: of the word before them (depth 2 only)
+        uint32_t d[5], fo[5];
+        d[1] = __vsub4(x[4], extract<16 - LB, false>(x));
+        d[2] = __vsub4(x[5], extract<20 - LB, false>(x));
+        d[3] = __vsub4(x[6], extract<24 - LB, false>(x));
+        d[4] = __vsub4(x[7], extract<28 - LB, false>(x));
+        if (depth2) d[0] = __vsub4(x[3], extract<12 - LB, false>(x));
+        {   // keys[0] is the difference comparison 0 expects ("pass" key): kept apart for the depth-2 refinement
             const uint32_t key = P.keys[0];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 1; k < 5; k++) {
                 const uint32_t t = d[k] ^ key;          // zero byte <=> difference == key
-                f[k] = (t - 0x01010101u) & ~t;          // bit 7 of a byte set if that byte (or a lower one) is zero
+                f[k - 1] = (t - 0x01010101u) & ~t;      // bit 7 of a byte set if that byte (or a lower one) is zero
+                fo[k] = 0;
             }
+            if (depth2) { const uint32_t t = d[0] ^ key; fo[0] = (t - 0x01010101u) & ~t; }
         }
         if (NK > 0) {
 #pragma unroll
             for (int j = 1; j < NK; j++) {
                 const uint32_t key = P.keys[j];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 1; k < 5; k++) {
                     const uint32_t t = d[k] ^ key;
-                    f[k] |= (t - 0x01010101u) & ~t;
+                    fo[k] |= (t - 0x01010101u) & ~t;
                 }
+                if (depth2) { const uint32_t t = d[0] ^ key; fo[0] |= (t - 0x01010101u) & ~t; }
             }
         } else {
 #pragma unroll 1
             for (int j = 1; j < nk; j++) {
                 const uint32_t key = P.keys[j];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 1; k < 5; k++) {
                     const uint32_t t = d[k] ^ key;
-                    f[k] |= (t - 0x01010101u) & ~t;
+                    fo[k] |= (t - 0x01010101u) & ~t;
                 }
+                if (depth2) { const uint32_t t = d[0] ^ key; fo[0] |= (t - 0x01010101u) & ~t; }
             }
         }
-        f[0] &= 0x80808080u; f[1] &= 0x80808080u; f[2] &= 0x80808080u; f[3] &= 0x80808080u;
+        if (!depth2) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) f[k] = (f[k] | fo[k + 1]) & 0x80808080u;
+        } else {
+            // Depth 2 (simple / value-scan patterns): a window whose comparison 0 PASSES (difference == keys[0]) can
+            // only be an event if its comparison 1 -- the difference one byte earlier -- is a key as well; every
+            // other such window advances by J0 without a match.  any[k]: "difference is a key" per byte.
+            uint32_t any[5];
+            any[0] = fo[0] & 0x80808080u;               // fo[0] already holds all keys of the word before
+#pragma unroll
+            for (int k = 1; k < 5; k++) any[k] = (f[k - 1] | fo[k]) & 0x80808080u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t earlier = __funnelshift_l(any[k], any[k + 1], 8);      // flag of the byte before
+                f[k] = ((fo[k + 1] & 0x80808080u) | (f[k] & earlier)) & 0x80808080u;
+            }
+        }
         return (f[0] | f[1] | f[2] | f[3]) != 0;
     } else {
         // t = cur + ~prev = (cur - prev - 1) per 16-bit half; key constant C = 1 - key;
@@ -410,6 +435,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
 
     WarpState st;
     st.cursor = reg_lo;
+    bool dense = false;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
 
     for (;;) {
@@ -476,6 +502,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 __syncwarp();
             }
             const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW, (len - rel_stage + MMG_ROW - 1) / MMG_ROW);
+            uint32_t stage_cands = 0;
             uint32_t sa = ring_a + slot * MMG_STAGE_STRIDE + (uint32_t)lane * 16u;
 #pragma unroll 1
             for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW) {
@@ -487,7 +514,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 uint32_t f[8];
                 bool any;
                 if (LB == 0) any = true;
-                else if (W == 1) any = filter_lane<1, LB, false, NK>(P, x, f);
+                else if (W == 1) any = filter_lane<1, LB, false, NK>(P, x, f, dense);
                 else any = prefilter16<LB, BE, NK>(P, x);
                 if (__any_sync(FULL, any)) {
                     // exact per-position flags (16-bit: only now), then ordered enqueue of the candidates
@@ -513,6 +540,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                         m &= m - 1;
                     }
                     qn += total;
+                    stage_cands += total;
                     __syncwarp();
                     uint32_t qh = 0;
                     while (qn - qh >= 32) {
@@ -534,6 +562,8 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
                             ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
             if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
+            // candidate-dense data (low entropy): switch the 8-bit filter to its depth-2 refinement
+            dense = LB == 1 && W == 1 && P.d2ok && stage_cands >= 48u;
         }
         if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
         __syncwarp();
@@ -971,10 +1001,20 @@ bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_by
 cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *blocks_per_sm) {
     const void *fn = filter_kernel(W, lag_bytes, be, nkeys);
     if (!fn) return cudaErrorInvalidValue;
+    // per (device, kernel) cache: the attribute call and the occupancy query cost microseconds per scan otherwise
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, fn});
+    if (it != cache.end()) { *blocks_per_sm = it->second; return cudaSuccess; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MMG_FILTER_WARPS * MMG_WARP_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, MMG_FILTER_WARPS * 32,
-                                                         MMG_FILTER_WARPS * MMG_WARP_SMEM);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, MMG_FILTER_WARPS * 32,
+                                                      MMG_FILTER_WARPS * MMG_WARP_SMEM);
+    if (e == cudaSuccess) cache[{dev, fn}] = *blocks_per_sm;
+    return e;
 }
 
 cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lag_bytes, int grid,
