@@ -191,32 +191,48 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
     } else {
         const int32_t cap0 = d.chk[0].cap;
         d.J0 = std::min(cap0, d.tab_default);
-        std::vector<uint32_t> keys;
-        auto add_key = [&](int32_t diff) {
-            if (!d.modular && (diff > vmax || diff < -vmax)) return;   // an exact difference the data cannot produce
-            uint32_t k = static_cast<uint32_t>(diff) & vmask;
-            if (std::find(keys.begin(), keys.end(), k) == keys.end()) keys.push_back(k);
-        };
-        add_key(d.chk[0].ed);
-        for (int j = 0; j < d.ntab; j++)
-            if (std::min(cap0, d.tab_val[j]) != d.J0) add_key(d.tab_key[j]);
-        d.nkeys = static_cast<int32_t>(keys.size());
-        // depth-2 refinement of the 8-bit filter: valid when comparisons 0 and 1 look at adjacent byte pairs with
-        // exact arithmetic, keys[0] is the pass key and no other key aliases it modulo 256 (scan_kernels.cu)
-        {
+        if (d.W == 1) {
+            // 8-bit filter keys are EXACT signed differences (scan_kernels.cu filter8).  keys[0] is the difference
+            // comparison 0 expects; in wildcard mode the comparison is modulo 256, so both signed values of that
+            // residue pass.  The other keys are the table entries whose advance differs from J0.
+            std::vector<int32_t> keys;
+            auto add_key = [&](int32_t diff) {
+                if (diff > vmax || diff < -vmax) return;                       // a difference the data cannot produce
+                if (std::find(keys.begin(), keys.end(), diff) == keys.end()) keys.push_back(diff);
+            };
             const int32_t ed0 = d.chk[0].ed;
-            bool ok = d.W == 1 && !d.modular && d.ncheck >= 2 && d.chk[0].lag == 1 && d.chk[1].lag == 1 &&
-                      d.chk[1].i == d.chk[0].i - 1 && ed0 <= vmax && ed0 >= -vmax && !keys.empty() &&
-                      keys[0] == (static_cast<uint32_t>(ed0) & vmask);
-            for (int j = 0; j < d.ntab && ok; j++)      // another key with the same residue would hide behind keys[0]
-                if (d.tab_key[j] != ed0 && ((static_cast<uint32_t>(d.tab_key[j]) ^ static_cast<uint32_t>(ed0)) & vmask) == 0 &&
-                    d.tab_key[j] <= vmax && d.tab_key[j] >= -vmax && std::min(cap0, d.tab_val[j]) != d.J0)
-                    ok = false;
-            d.d2ok = ok ? 1 : 0;
-        }
-        for (size_t j = 0; j < keys.size(); j++) {
-            d.keys[j] = d.W == 1 ? keys[j] * 0x01010101u : ((1u - keys[j]) & 0xFFFFu) * 0x00010001u;
-            d.pkeys[j] = (((1u - keys[j]) & 0xFFFFu) << 16) | ((0u - keys[j]) & 0xFFFFu);
+            if (d.modular) {
+                const int32_t r = static_cast<int32_t>(static_cast<uint32_t>(ed0) & vmask);
+                add_key(r);
+                if (r != 0) add_key(r - 256);
+            } else {
+                add_key(ed0);
+            }
+            const bool pass_first = !keys.empty() && keys[0] == ed0;
+            for (int j = 0; j < d.ntab; j++)
+                if (std::min(cap0, d.tab_val[j]) != d.J0) add_key(d.tab_key[j]);
+            d.nkeys = static_cast<int32_t>(keys.size());
+            if (d.nkeys == 0) { keys.push_back(1 << 20); d.nkeys = 1; }        // nothing can ever be flagged: one impossible key
+            // depth-2 refinement: comparisons 0 and 1 look at adjacent element pairs with exact arithmetic
+            d.d2ok = (!d.modular && d.ncheck >= 2 && d.chk[0].lag == 1 && d.chk[1].lag == 1 &&
+                      d.chk[1].i == d.chk[0].i - 1 && pass_first) ? 1 : 0;
+            for (size_t j = 0; j < keys.size(); j++)
+                d.keys[j] = ((0x10000u - 256u - static_cast<uint32_t>(keys[j])) & 0xFFFFu) * 0x00010001u;
+        } else {
+            std::vector<uint32_t> keys;
+            auto add_key = [&](int32_t diff) {
+                if (!d.modular && (diff > vmax || diff < -vmax)) return;   // an exact difference the data cannot produce
+                uint32_t k = static_cast<uint32_t>(diff) & vmask;
+                if (std::find(keys.begin(), keys.end(), k) == keys.end()) keys.push_back(k);
+            };
+            add_key(d.chk[0].ed);
+            for (int j = 0; j < d.ntab; j++)
+                if (std::min(cap0, d.tab_val[j]) != d.J0) add_key(d.tab_key[j]);
+            d.nkeys = static_cast<int32_t>(keys.size());
+            for (size_t j = 0; j < keys.size(); j++) {
+                d.keys[j] = ((1u - keys[j]) & 0xFFFFu) * 0x00010001u;
+                d.pkeys[j] = (((1u - keys[j]) & 0xFFFFu) << 16) | ((0u - keys[j]) & 0xFFFFu);
+            }
         }
     }
 

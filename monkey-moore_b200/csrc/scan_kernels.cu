@@ -8,6 +8,7 @@
 #include "scan_kernels.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -75,64 +76,7 @@ __device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t 
     if (LB == 0) return true;   // evaluate-everything mode
     const int nk = NK > 0 ? NK : P.nkeys;
     if (W == 1) {
-        // d[1..4]: byte-wise differences of this lane's four words; d[0]: of the word before them (depth 2 only)
-        uint32_t d[5], fo[5];
-        d[1] = __vsub4(x[4], extract<16 - LB, false>(x));
-        d[2] = __vsub4(x[5], extract<20 - LB, false>(x));
-        d[3] = __vsub4(x[6], extract<24 - LB, false>(x));
-        d[4] = __vsub4(x[7], extract<28 - LB, false>(x));
-        if (depth2) d[0] = __vsub4(x[3], extract<12 - LB, false>(x));
-        {   // keys[0] is the difference comparison 0 expects ("pass" key): kept apart for the depth-2 refinement
-            const uint32_t key = P.keys[0];
-#pragma unroll
-            for (int k = 1; k < 5; k++) {
-                const uint32_t t = d[k] ^ key;          // zero byte <=> difference == key
-                f[k - 1] = (t - 0x01010101u) & ~t;      // bit 7 of a byte set if that byte (or a lower one) is zero
-                fo[k] = 0;
-            }
-            if (depth2) { const uint32_t t = d[0] ^ key; fo[0] = (t - 0x01010101u) & ~t; }
-        }
-        if (NK > 0) {
-#pragma unroll
-            for (int j = 1; j < NK; j++) {
-                const uint32_t key = P.keys[j];
-#pragma unroll
-                for (int k = 1; k < 5; k++) {
-                    const uint32_t t = d[k] ^ key;
-                    fo[k] |= (t - 0x01010101u) & ~t;
-                }
-                if (depth2) { const uint32_t t = d[0] ^ key; fo[0] |= (t - 0x01010101u) & ~t; }
-            }
-        } else {
-#pragma unroll 1
-            for (int j = 1; j < nk; j++) {
-                const uint32_t key = P.keys[j];
-#pragma unroll
-                for (int k = 1; k < 5; k++) {
-                    const uint32_t t = d[k] ^ key;
-                    fo[k] |= (t - 0x01010101u) & ~t;
-                }
-                if (depth2) { const uint32_t t = d[0] ^ key; fo[0] |= (t - 0x01010101u) & ~t; }
-            }
-        }
-        if (!depth2) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) f[k] = (f[k] | fo[k + 1]) & 0x80808080u;
-        } else {
-            // Depth 2 (simple / value-scan patterns): a window whose comparison 0 PASSES (difference == keys[0]) can
-            // only be an event if its comparison 1 -- the difference one byte earlier -- is a key as well; every
-            // other such window advances by J0 without a match.  any[k]: "difference is a key" per byte.
-            uint32_t any[5];
-            any[0] = fo[0] & 0x80808080u;               // fo[0] already holds all keys of the word before
-#pragma unroll
-            for (int k = 1; k < 5; k++) any[k] = (f[k - 1] | fo[k]) & 0x80808080u;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t earlier = __funnelshift_l(any[k], any[k + 1], 8);      // flag of the byte before
-                f[k] = ((fo[k + 1] & 0x80808080u) | (f[k] & earlier)) & 0x80808080u;
-            }
-        }
-        return (f[0] | f[1] | f[2] | f[3]) != 0;
+        return true;    // 8-bit searches use filter8() below
     } else {
         // t = cur + ~prev = (cur - prev - 1) per 16-bit half; key constant C = 1 - key;
         // min-accumulate t + C: a zero half <=> difference == key
@@ -156,6 +100,108 @@ __device__ __forceinline__ bool filter_lane(const MmgProgram &P, const uint32_t 
                               __vminu2(__vminu2(f[4], f[5]), __vminu2(f[6], f[7])));
         return ((m & 0xFFFFu) == 0) || ((m >> 16) == 0);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 8-bit filter: the lane's 16 elements (and the 16 before them) are unpacked into 16-bit pairs so that the
+// differences are EXACT signed values (one IADD3 per pair, bias 256 keeps both halves positive) and one
+// VIADDMNMX.U16x2 per key and pair min-accumulates "difference - key": a zero half <=> that element's
+// comparison-0 difference is a key.  Pair registers: E[q] = elements (4q, 4q+2) of word q, O[q] = (4q+1, 4q+3).
+// ------------------------------------------------------------------------------------------
+
+template <int POS>
+__device__ __forceinline__ uint32_t pair_at(const uint32_t (&E)[8], const uint32_t (&O)[8]) {
+    // elements at byte POS and POS + 2 of the 32-byte window, as (low half, high half)
+    constexpr int q = POS >> 2, r = POS & 3;
+    if (r == 0) return E[q];
+    if (r == 1) return O[q];
+    if (r == 2) return __funnelshift_r(E[q], E[q + 1 < 8 ? q + 1 : q], 16);
+    return __funnelshift_r(O[q], O[q + 1 < 8 ? q + 1 : q], 16);
+}
+
+template <int LB, int POS>
+__device__ __forceinline__ uint32_t diff_at(const uint32_t (&E)[8], const uint32_t (&O)[8]) {
+    return pair_at<POS>(E, O) - pair_at<POS - LB>(E, O) + 0x01000100u;      // halves: 256 + (cur - prv), never a borrow
+}
+
+// Returns the 16-bit candidate mask of the lane: bit e <=> the element at the lane's own byte e is flagged.
+// NK > 0: compile-time key count.  DEPTH2 (simple / value-scan patterns, P.d2ok): a window whose comparison 0
+// PASSES (difference == keys[0]) is kept only if its comparison 1 -- the difference one element earlier -- is
+// a key as well; every other such window advances by J0 without a match, i.e. is not an event.
+template <int LB, int NK, bool DEPTH2>
+__device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t (&x)[8]) {
+    uint32_t E[8], O[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { E[q] = x[q] & 0x00FF00FFu; O[q] = __byte_perm(x[q], 0u, 0x4341u); }
+    // D[1 + 2q + t]: pair (4q + t, 4q + t + 2) of the lane's own bytes; D[0]: pair (-3, -1) (DEPTH2 only)
+    uint32_t D[9];
+    D[1] = diff_at<LB, 16>(E, O); D[2] = diff_at<LB, 17>(E, O); D[3] = diff_at<LB, 20>(E, O); D[4] = diff_at<LB, 21>(E, O);
+    D[5] = diff_at<LB, 24>(E, O); D[6] = diff_at<LB, 25>(E, O); D[7] = diff_at<LB, 28>(E, O); D[8] = diff_at<LB, 29>(E, O);
+    if (DEPTH2) D[0] = diff_at<LB, 13>(E, O);
+    const int nk = NK > 0 ? NK : P.nkeys;
+    uint32_t c[9];          // zero half <=> candidate
+    if (!DEPTH2) {
+        const uint32_t k0 = P.keys[0];
+#pragma unroll
+        for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], k0, 0xFFFFFFFFu);      // per-half add: no carry across
+        if (NK > 0) {
+#pragma unroll
+            for (int j = 1; j < NK; j++) {
+                const uint32_t kj = P.keys[j];
+#pragma unroll
+                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], kj, c[k]);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 1; j < nk; j++) {
+                const uint32_t kj = P.keys[j];
+#pragma unroll
+                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], kj, c[k]);
+            }
+        }
+    } else {
+        uint32_t ap[9], ao[9];      // pass key / the other keys
+        const uint32_t k0 = P.keys[0];
+#pragma unroll
+        for (int k = 0; k < 9; k++) { ap[k] = __viaddmin_u16x2(D[k], k0, 0xFFFFFFFFu); ao[k] = 0xFFFFFFFFu; }
+        if (NK > 0) {
+#pragma unroll
+            for (int j = 1; j < NK; j++) {
+                const uint32_t kj = P.keys[j];
+#pragma unroll
+                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], kj, ao[k]);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 1; j < nk; j++) {
+                const uint32_t kj = P.keys[j];
+#pragma unroll
+                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], kj, ao[k]);
+            }
+        }
+        // any[k]: zero half <=> that element's difference is some key
+        uint32_t any[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) any[k] = NK == 1 ? ap[k] : __vminu2(ap[k], ao[k]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            // the element before (4q, 4q+2) is (4q-1, 4q+1): upper half of the O pair of word q-1, lower half of word q's
+            const uint32_t before_e = __funnelshift_r(any[2 * q], any[2 * q + 2], 16);
+            const uint32_t before_o = any[2 * q + 1];                            // before (4q+1, 4q+3) is (4q, 4q+2)
+            const uint32_t pe = __vmaxu2(ap[2 * q + 1], before_e), po = __vmaxu2(ap[2 * q + 2], before_o);
+            c[2 * q + 1] = NK == 1 ? pe : __vminu2(ao[2 * q + 1], pe);
+            c[2 * q + 2] = NK == 1 ? po : __vminu2(ao[2 * q + 2], po);
+        }
+    }
+    // halves -> bits: a non-candidate half becomes 1, weighted so that bit e (and 14 + e for the upper halves) names element e
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        m += __vminu2(c[2 * q + 1], 0x00010001u) << (4 * q);
+        m += __vminu2(c[2 * q + 2], 0x00010001u) << (4 * q + 1);
+    }
+    return ((m | (m >> 14)) & 0xFFFFu) ^ 0xFFFFu;
 }
 
 // 16-bit candidate mask in ascending byte order.  Bit b names the element whose first byte is
@@ -246,6 +292,8 @@ struct SProg {
     int32_t ced[MMG_MAXL], ccap[MMG_MAXL];
     int32_t tkey[MMG_MAXL], tval[MMG_MAXL];
     uint8_t tab8[512];      // 8-bit searches: skip for every possible difference d, indexed d + 255
+    uint8_t tab0[512];      // ditto with the cap of comparison 0 applied: the advance when comparison 0 fails on d
+    uint8_t tab1[512];      // ditto for comparison 1
 };
 __shared__ SProg g_sprog;
 
@@ -264,6 +312,8 @@ __device__ __forceinline__ void load_sprog(const MmgProgram &P) {
             for (int j = 0; j < P.ntab; j++)
                 if (P.tab_key[j] == i - 255) sk = P.tab_val[j];
             g_sprog.tab8[i] = (uint8_t)sk;
+            g_sprog.tab0[i] = (uint8_t)min(sk, P.ncheck > 0 ? P.chk[0].cap : sk);
+            g_sprog.tab1[i] = (uint8_t)min(sk, P.ncheck > 1 ? P.chk[1].cap : sk);
         }
     }
     __syncthreads();
@@ -411,6 +461,52 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int lds16s(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
+// F(s) of an 8-bit window that lies in shared memory at address wa, from comparison c0 on (the earlier ones
+// passed).  sp: shared address of g_sprog.  32-bit shared addresses throughout.
+__device__ __noinline__ uint32_t eval_window_lds8(uint32_t wa, uint32_t sp, int c0, uint32_t pmask) {
+    const int nc = lds32(sp + (uint32_t)offsetof(SProg, ncheck));
+    for (int c = c0; c < nc; c++) {
+        const int i = lds16s(sp + (uint32_t)offsetof(SProg, ci) + 2u * c);
+        const int lag = lds16s(sp + (uint32_t)offsetof(SProg, clag) + 2u * c);
+        const int d = (int)lds8(wa + i) - (int)lds8(wa + i - lag);
+        const int ed = lds32(sp + (uint32_t)offsetof(SProg, ced) + 4u * c);
+        if ((((uint32_t)(d - ed)) & pmask) != 0u) {
+            const int sk = (int)lds8(sp + (uint32_t)offsetof(SProg, tab8) + 255u + d);
+            return (uint32_t)min(lds32(sp + (uint32_t)offsetof(SProg, ccap) + 4u * c), sk);
+        }
+    }
+    return 0x100u | (uint32_t)lds32(sp + (uint32_t)offsetof(SProg, match_jump));
+}
+
+// record the extent of sub-tile t's event list: [st.open_start, cut)
+__device__ __forceinline__ WarpState close_at(const MmgScratch &X, WarpState st, uint32_t t, uint32_t cut, int lane) {
+    if (lane == 0 && cut != st.open_start) {
+        X.sub_start[t] = st.open_start;
+        X.sub_count[t] = cut - st.open_start;
+        X.hasev[t] = 1;
+    }
+    st.open_start = cut;
+    st.open_t = t + 1;
+    return st;
+}
+
 template <int W, int LB, bool BE, int NK>
 __global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER_MIN_CTAS)
 k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
@@ -432,6 +528,15 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
+
+    // exact evaluation of the 8-bit candidates: comparisons 0 and 1 from registers, tables through 32-bit shared addresses
+    constexpr bool DIRECT = W == 1 && LB != 0;
+    const int ev_ed0 = P.chk[0].ed, ev_ed1 = P.chk[1].ed, ev_L = P.L, ev_nc = P.ncheck;
+    const uint32_t ev_pmask = P.modular ? 0xFFu : 0xFFFFFFFFu;
+    const uint32_t ev_o1c = (uint32_t)(P.chk[0].i - P.chk[1].i), ev_o1p = ev_o1c + (uint32_t)P.chk[1].lag;
+    const uint32_t ev_match = 0x100u | (uint32_t)P.match_jump;
+    const uint32_t sprog_a = smem_u32(&g_sprog);
+    const uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
 
     WarpState st;
     st.cursor = reg_lo;
@@ -486,6 +591,14 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         const bool at_start = p0 == 0;
         C.q_base = (int64_t)p0 - sigma - (W == 2 ? 1 : 0);
         uint32_t qn = 0;
+        // direct path (8-bit): a candidate at chunk-relative position rel (current element of comparison 0) is a
+        // valid window iff sg <= rel < v_hi   (window start = rel - sg inside the chunk and inside the block's view)
+        const uint32_t sg = (uint32_t)sigma;
+        uint32_t v_hi = 0;
+        {
+            const int64_t lim = min((int64_t)(C.s_hi - C.s_lo), C.blk_off + C.max_rel[0] + 1 - (int64_t)p0);
+            if (lim > 0) v_hi = (uint32_t)lim + sg;
+        }
 
         if (lane == 0) {
             uint32_t sl = slot;
@@ -503,6 +616,8 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
             }
             const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW, (len - rel_stage + MMG_ROW - 1) / MMG_ROW);
             uint32_t stage_cands = 0;
+            // bytes of this stage that the bulk copy filled (exact evaluation from shared memory stays inside them)
+            const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE_BYTES, copy_end_rel - rel_stage) : 0u;
             uint32_t sa = ring_a + slot * MMG_STAGE_STRIDE + (uint32_t)lane * 16u;
 #pragma unroll 1
             for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW) {
@@ -511,11 +626,69 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 uint32_t x[8];
                 x[0] = prv.x; x[1] = prv.y; x[2] = prv.z; x[3] = prv.w;
                 x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
+                if (DIRECT) {
+                    // ---- 8-bit direct path: every candidate becomes an event word in place (no queue).  A candidate
+                    // whose comparison 0 fails takes its advance from the table; one that passes goes on to comparison 1
+                    // (and, rarely, further).  Flagged windows that turn out to advance by J0 without a match are
+                    // written as "null" events: a no-op in the replay.
+                    const uint32_t rowrel = rel_stage + r * MMG_ROW;
+                    const bool boundary = (rowrel & (MMG_SUBTILE - 1)) == 0 && rowrel != 0;
+                    uint32_t cm = dense ? filter8<(LB ? LB : 1), NK, true>(P, x) : filter8<(LB ? LB : 1), NK, false>(P, x);
+                    const uint32_t lanerel = rowrel + (uint32_t)lane * 16u;
+                    if (rowrel < sg || rowrel + MMG_ROW > v_hi) {               // edge row: clip to the valid windows
+                        const int lo = max((int)sg - (int)lanerel, 0), hi = min((int)v_hi - (int)lanerel, 16);
+                        cm = (hi <= lo) ? 0u : (cm & ((1u << hi) - 1u) & ~((1u << lo) - 1u));
+                    }
+                    const uint32_t cnt = __popc(cm);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const uint32_t b0 = __ballot_sync(FULL, cnt & 1u), b1 = __ballot_sync(FULL, cnt & 2u);
+                    uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
+                    uint32_t total = __popc(b0) + 2u * __popc(b1);
+                    if (__any_sync(FULL, cnt >= 4u)) {
+                        const uint32_t b2 = __ballot_sync(FULL, cnt & 4u), b3 = __ballot_sync(FULL, cnt & 8u),
+                                       b4 = __ballot_sync(FULL, cnt & 16u);
+                        pre += 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt) + 16u * __popc(b4 & lt);
+                        total += 4u * __popc(b2) + 8u * __popc(b3) + 16u * __popc(b4);
+                    }
+                    if (boundary) {     // candidates below rowrel + sg still belong to the previous sub-tile
+                        const int bl = min(max((int)(rowrel + sg) - (int)lanerel, 0), 16);
+                        const uint32_t nbefore = __reduce_add_sync(FULL, __popc(cm & ((1u << bl) - 1u)));
+                        st = close_at(X, st, t0 + (rowrel >> MMG_SUBTILE_SHIFT) - 1u, st.cursor + nbefore, lane);
+                    }
+                    uint32_t at = st.cursor + pre;
+                    while (cm) {
+                        const uint32_t b = (uint32_t)__ffs(cm) - 1u;
+                        cm &= cm - 1u;
+                        const uint32_t ca = sa + 16u + b;                       // current element of comparison 0
+                        const int dd = (int)lds8(ca) - (int)lds8(ca - LB);
+                        const uint32_t ws = lanerel + b - sg;                   // window start, chunk relative
+                        uint32_t res;
+                        if ((((uint32_t)(dd - ev_ed0)) & ev_pmask) != 0u) {
+                            res = lds8(tab0_a + dd);
+                        } else if (ev_nc == 1) {
+                            res = ev_match;
+                        } else {
+                            const int wrel = (int)ws - (int)rel_stage;          // the window usually lies in this stage's buffer
+                            if (wrel >= -16 && wrel + ev_L <= (int)stage_fill) {
+                                const int d1 = (int)lds8(ca - ev_o1c) - (int)lds8(ca - ev_o1p);
+                                if ((((uint32_t)(d1 - ev_ed1)) & ev_pmask) != 0u) res = lds8(tab1_a + d1);
+                                else if (ev_nc == 2) res = ev_match;
+                                else res = eval_window_lds8(ring_a + slot * MMG_STAGE_STRIDE + 16u + (uint32_t)wrel, sprog_a, 2, ev_pmask);
+                            } else {
+                                res = eval_window<1, false>(P, chunk_base + ws);
+                            }
+                        }
+                        if (at < C.reg_hi) C.ev[at] = (ws & (MMG_SUBTILE - 1)) | (res << 16);   // 0x100 << 16 == MMG_EV_MATCH
+                        at++;
+                    }
+                    st.cursor += total;
+                    stage_cands += total;
+                    continue;
+                }
                 uint32_t f[8];
                 bool any;
                 if (LB == 0) any = true;
-                else if (W == 1) any = filter_lane<1, LB, false, NK>(P, x, f, dense);
-                else any = prefilter16<LB, BE, NK>(P, x);
+                else if (W == 2) any = prefilter16<LB, BE, NK>(P, x);
                 if (__any_sync(FULL, any)) {
                     // exact per-position flags (16-bit: only now), then ordered enqueue of the candidates
                     if (LB != 0 && W == 2) any = any && filter_lane<2, LB, BE, 0>(P, x, f);
@@ -565,9 +738,14 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
             // candidate-dense data (low entropy): switch the 8-bit filter to its depth-2 refinement
             dense = LB == 1 && W == 1 && P.d2ok && stage_cands >= 48u;
         }
-        if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
-        __syncwarp();
-        st = close_until(X, st, t1, lane);
+        if (DIRECT) {
+            // the row at chunk-relative 4096 * (t1 - t0) closed the last sub-tile unless the data ended before it
+            if (st.open_t < t1) st = close_at(X, st, st.open_t, st.cursor, lane);
+        } else {
+            if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+            __syncwarp();
+            st = close_until(X, st, t1, lane);
+        }
     }
     if (lane == 0) {
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
