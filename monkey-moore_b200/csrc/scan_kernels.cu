@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t diff_at(const uint32_t (&E)[8], const uint32
 // PASSES (difference == keys[0]) is kept only if its comparison 1 -- the difference one element earlier -- is
 // a key as well; every other such window advances by J0 without a match, i.e. is not an event.
 template <int LB, int NK, bool DEPTH2>
-__device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t (&x)[8]) {
+__device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t *x) {
     uint32_t E[8], O[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) { E[q] = x[q] & 0x00FF00FFu; O[q] = __byte_perm(x[q], 0u, 0x4341u); }
@@ -529,18 +529,8 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
 
-    // exact evaluation of the 8-bit candidates: comparisons 0 and 1 from registers, tables through 32-bit shared addresses
-    constexpr bool DIRECT = W == 1 && LB != 0;
-    const int ev_ed0 = P.chk[0].ed, ev_ed1 = P.chk[1].ed, ev_L = P.L, ev_nc = P.ncheck;
-    const uint32_t ev_pmask = P.modular ? 0xFFu : 0xFFFFFFFFu;
-    const uint32_t ev_o1c = (uint32_t)(P.chk[0].i - P.chk[1].i), ev_o1p = ev_o1c + (uint32_t)P.chk[1].lag;
-    const uint32_t ev_match = 0x100u | (uint32_t)P.match_jump;
-    const uint32_t sprog_a = smem_u32(&g_sprog);
-    const uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
-
     WarpState st;
     st.cursor = reg_lo;
-    bool dense = false;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
 
     for (;;) {
@@ -591,15 +581,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         const bool at_start = p0 == 0;
         C.q_base = (int64_t)p0 - sigma - (W == 2 ? 1 : 0);
         uint32_t qn = 0;
-        // direct path (8-bit): a candidate at chunk-relative position rel (current element of comparison 0) is a
-        // valid window iff sg <= rel < v_hi   (window start = rel - sg inside the chunk and inside the block's view)
-        const uint32_t sg = (uint32_t)sigma;
-        uint32_t v_hi = 0;
-        {
-            const int64_t lim = min((int64_t)(C.s_hi - C.s_lo), C.blk_off + C.max_rel[0] + 1 - (int64_t)p0);
-            if (lim > 0) v_hi = (uint32_t)lim + sg;
-        }
-
         if (lane == 0) {
             uint32_t sl = slot;
             for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
@@ -615,9 +596,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 __syncwarp();
             }
             const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW, (len - rel_stage + MMG_ROW - 1) / MMG_ROW);
-            uint32_t stage_cands = 0;
-            // bytes of this stage that the bulk copy filled (exact evaluation from shared memory stays inside them)
-            const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE_BYTES, copy_end_rel - rel_stage) : 0u;
             uint32_t sa = ring_a + slot * MMG_STAGE_STRIDE + (uint32_t)lane * 16u;
 #pragma unroll 1
             for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW) {
@@ -626,65 +604,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 uint32_t x[8];
                 x[0] = prv.x; x[1] = prv.y; x[2] = prv.z; x[3] = prv.w;
                 x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
-                if (DIRECT) {
-                    // ---- 8-bit direct path: every candidate becomes an event word in place (no queue).  A candidate
-                    // whose comparison 0 fails takes its advance from the table; one that passes goes on to comparison 1
-                    // (and, rarely, further).  Flagged windows that turn out to advance by J0 without a match are
-                    // written as "null" events: a no-op in the replay.
-                    const uint32_t rowrel = rel_stage + r * MMG_ROW;
-                    const bool boundary = (rowrel & (MMG_SUBTILE - 1)) == 0 && rowrel != 0;
-                    uint32_t cm = dense ? filter8<(LB ? LB : 1), NK, true>(P, x) : filter8<(LB ? LB : 1), NK, false>(P, x);
-                    const uint32_t lanerel = rowrel + (uint32_t)lane * 16u;
-                    if (rowrel < sg || rowrel + MMG_ROW > v_hi) {               // edge row: clip to the valid windows
-                        const int lo = max((int)sg - (int)lanerel, 0), hi = min((int)v_hi - (int)lanerel, 16);
-                        cm = (hi <= lo) ? 0u : (cm & ((1u << hi) - 1u) & ~((1u << lo) - 1u));
-                    }
-                    const uint32_t cnt = __popc(cm);
-                    const uint32_t lt = (1u << lane) - 1u;
-                    const uint32_t b0 = __ballot_sync(FULL, cnt & 1u), b1 = __ballot_sync(FULL, cnt & 2u);
-                    uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt);
-                    uint32_t total = __popc(b0) + 2u * __popc(b1);
-                    if (__any_sync(FULL, cnt >= 4u)) {
-                        const uint32_t b2 = __ballot_sync(FULL, cnt & 4u), b3 = __ballot_sync(FULL, cnt & 8u),
-                                       b4 = __ballot_sync(FULL, cnt & 16u);
-                        pre += 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt) + 16u * __popc(b4 & lt);
-                        total += 4u * __popc(b2) + 8u * __popc(b3) + 16u * __popc(b4);
-                    }
-                    if (boundary) {     // candidates below rowrel + sg still belong to the previous sub-tile
-                        const int bl = min(max((int)(rowrel + sg) - (int)lanerel, 0), 16);
-                        const uint32_t nbefore = __reduce_add_sync(FULL, __popc(cm & ((1u << bl) - 1u)));
-                        st = close_at(X, st, t0 + (rowrel >> MMG_SUBTILE_SHIFT) - 1u, st.cursor + nbefore, lane);
-                    }
-                    uint32_t at = st.cursor + pre;
-                    while (cm) {
-                        const uint32_t b = (uint32_t)__ffs(cm) - 1u;
-                        cm &= cm - 1u;
-                        const uint32_t ca = sa + 16u + b;                       // current element of comparison 0
-                        const int dd = (int)lds8(ca) - (int)lds8(ca - LB);
-                        const uint32_t ws = lanerel + b - sg;                   // window start, chunk relative
-                        uint32_t res;
-                        if ((((uint32_t)(dd - ev_ed0)) & ev_pmask) != 0u) {
-                            res = lds8(tab0_a + dd);
-                        } else if (ev_nc == 1) {
-                            res = ev_match;
-                        } else {
-                            const int wrel = (int)ws - (int)rel_stage;          // the window usually lies in this stage's buffer
-                            if (wrel >= -16 && wrel + ev_L <= (int)stage_fill) {
-                                const int d1 = (int)lds8(ca - ev_o1c) - (int)lds8(ca - ev_o1p);
-                                if ((((uint32_t)(d1 - ev_ed1)) & ev_pmask) != 0u) res = lds8(tab1_a + d1);
-                                else if (ev_nc == 2) res = ev_match;
-                                else res = eval_window_lds8(ring_a + slot * MMG_STAGE_STRIDE + 16u + (uint32_t)wrel, sprog_a, 2, ev_pmask);
-                            } else {
-                                res = eval_window<1, false>(P, chunk_base + ws);
-                            }
-                        }
-                        if (at < C.reg_hi) C.ev[at] = (ws & (MMG_SUBTILE - 1)) | (res << 16);   // 0x100 << 16 == MMG_EV_MATCH
-                        at++;
-                    }
-                    st.cursor += total;
-                    stage_cands += total;
-                    continue;
-                }
                 uint32_t f[8];
                 bool any;
                 if (LB == 0) any = true;
@@ -713,7 +632,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                         m &= m - 1;
                     }
                     qn += total;
-                    stage_cands += total;
                     __syncwarp();
                     uint32_t qh = 0;
                     while (qn - qh >= 32) {
@@ -735,17 +653,203 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                 issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
                             ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
             if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
-            // candidate-dense data (low entropy): switch the 8-bit filter to its depth-2 refinement
-            dense = LB == 1 && W == 1 && P.d2ok && stage_cands >= 48u;
         }
-        if (DIRECT) {
-            // the row at chunk-relative 4096 * (t1 - t0) closed the last sub-tile unless the data ended before it
-            if (st.open_t < t1) st = close_at(X, st, st.open_t, st.cursor, lane);
-        } else {
-            if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+        if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+        __syncwarp();
+        st = close_until(X, st, t1, lane);
+    }
+    if (lane == 0) {
+        atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
+        atomicAdd((unsigned long long *)&X.status[1], (unsigned long long)(st.cursor - reg_lo));
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K1 (8-bit): same per-warp TMA ring as k_filter, but every lane owns 32 contiguous bytes of a 1 KiB row, the
+// candidates of a row are compacted with one warp scan and each becomes an event word in place (no queue):
+//   * comparison 0 fails (the usual case): the advance comes from a 511-entry table in shared memory;
+//   * it passes: comparison 1 is evaluated from the row in shared memory, deeper ones (rare) by a helper.
+// Flagged windows that turn out to advance by J0 without a match are written as "null" events (a no-op in the
+// replay), so the event offsets can be assigned before the evaluation.
+// ------------------------------------------------------------------------------------------
+
+#define MMG_ROW8 1024u
+
+template <int LB, int NK>
+__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER_MIN_CTAS)
+k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * MMG_FILTER_WARPS + wib;
+    const uint32_t reg_lo = warp * X.ev_per_warp, reg_hi = reg_lo + X.ev_per_warp;
+
+    uint8_t *ring = smem_raw + (size_t)wib * MMG_WARP_SMEM;
+    const uint32_t ring_a = smem_u32(ring);
+    const uint32_t bar_a = ring_a + MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u;
+    if (lane == 0) {
+        for (int i = 0; i < MMG_NSTAGES; i++) mbar_init(bar_a + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    load_sprog(P);      // includes the only __syncthreads() of the kernel
+
+    // constants of the exact evaluation, pinned in registers (the empty asm keeps ptxas from re-deriving them per use)
+    uint32_t sg = (uint32_t)P.chk[0].i;                  // window start = position of comparison 0's current element - sg
+    int ev_ed0 = P.chk[0].ed, ev_ed1 = P.chk[1].ed;
+    const int ev_L = P.L, ev_nc = P.ncheck;
+    uint32_t ev_pmask = P.modular ? 0xFFu : 0xFFFFFFFFu;
+    const uint32_t ev_o1c = (uint32_t)(P.chk[0].i - P.chk[1].i), ev_o1p = ev_o1c + (uint32_t)P.chk[1].lag;
+    const uint32_t ev_match = 0x100u | (uint32_t)P.match_jump;
+    uint32_t sprog_a = smem_u32(&g_sprog);
+    asm volatile("" : "+r"(sprog_a), "+r"(sg), "+r"(ev_ed0), "+r"(ev_pmask), "+r"(lane));
+    const uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const bool d2ok = P.d2ok != 0;
+
+    WarpState st;
+    st.cursor = reg_lo;
+    uint32_t dense_left = 0;          // stages the depth-2 refinement stays on before the candidate density is probed again
+    uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
+
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        if (chunk >= G.nchunks) break;
+
+        const uint32_t t0 = chunk * G.chunk_subs;
+        const uint32_t t1 = min(t0 + G.chunk_subs, G.nsub);
+        const uint64_t blk_off = (uint64_t)(t0 / G.spb) * G.B;
+        const uint64_t blk_size = min(G.B + (uint64_t)G.ov, G.S - blk_off);      // src/core/search_engine.cpp:227-230
+        const uint64_t p0 = (uint64_t)t0 << MMG_SUBTILE_SHIFT;                    // first window start of the chunk
+        const uint32_t chunk_bytes = (t1 - t0) << MMG_SUBTILE_SHIFT;
+        st.open_t = t0;
+        st.open_start = st.cursor;
+
+        // a candidate at chunk-relative position rel (current element of comparison 0) is a valid window iff
+        // sg <= rel < v_hi: the window starts inside the chunk and is complete inside the block's view
+        uint32_t v_hi = 0;
+        if (blk_size >= (uint64_t)ev_L) {
+            const int64_t lim = min((int64_t)chunk_bytes, (int64_t)(blk_off + blk_size - (uint64_t)ev_L + 1) - (int64_t)p0);
+            if (lim > 0) v_hi = (uint32_t)lim + sg;
+        }
+        const uint64_t s16 = (G.S + 15) & ~(uint64_t)15;
+        const uint64_t p_end = min(p0 + chunk_bytes + sg + 1, s16);
+        const uint32_t len = p_end > p0 ? (uint32_t)(p_end - p0) : 0u;            // bytes of position space to process
+        const uint32_t nst = (len + MMG_STAGE_BYTES - 1) / MMG_STAGE_BYTES;
+        const uint64_t aligned_end = G.S & ~(uint64_t)15;
+        const uint64_t want_end = min((p_end + 15) & ~(uint64_t)15, aligned_end);
+        const uint32_t copy_end_rel = want_end > p0 ? (uint32_t)(want_end - p0) : 0u;
+        const bool has_tail = aligned_end != G.S && aligned_end >= p0 && aligned_end < p0 + len;
+        const uint32_t tail_rel = has_tail ? (uint32_t)(aligned_end - p0) : 0xFFFFFFFFu;
+        const uint8_t *chunk_base = G.data + p0;
+        const bool at_start = p0 == 0;
+
+        if (lane == 0) {
+            uint32_t sl = slot;
+            for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
+                issue_stage(chunk_base, at_start, k * MMG_STAGE_BYTES, copy_end_rel, ring_a + sl * MMG_STAGE_STRIDE, bar_a + 8 * sl);
+                sl = sl + 1 == MMG_NSTAGES ? 0 : sl + 1;
+            }
+        }
+        for (uint32_t k = 0, rel_stage = 0; k < nst; k++, rel_stage += MMG_STAGE_BYTES) {
+            mbar_wait(bar_a + 8 * slot, parity);
+            if (tail_rel - rel_stage < MMG_STAGE_BYTES) {      // patch the last (S mod 16) bytes of the slice
+                if (lane < 16 && aligned_end + lane < G.S)
+                    ring[slot * MMG_STAGE_STRIDE + 16 + (tail_rel - rel_stage) + lane] = G.data[aligned_end + lane];
+                __syncwarp();
+            }
+            // bytes of this stage that the bulk copy filled (exact evaluation from shared memory stays inside them)
+            const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE_BYTES, copy_end_rel - rel_stage) : 0u;
+            const uint32_t stage_a = ring_a + slot * MMG_STAGE_STRIDE;
+            const bool stage_edge = rel_stage < sg || rel_stage + MMG_STAGE_BYTES > v_hi;
+            const bool dense = dense_left != 0;
+            const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW8, (len - rel_stage + MMG_ROW8 - 1) / MMG_ROW8);
+            uint32_t stage_cands = 0;
+#pragma unroll 1
+            for (uint32_t r = 0; r < rows; r++) {
+                const uint32_t rowrel = rel_stage + r * MMG_ROW8;
+                const uint32_t sa = stage_a + r * MMG_ROW8 + (uint32_t)lane * 32u;      // the 16 bytes before the lane's own 32
+                const uint32_t lanerel = rowrel + (uint32_t)lane * 32u;
+                uint32_t x[12];
+                {
+                    const uint4 a = lds128(sa), b = lds128(sa + 16), c = lds128(sa + 32);
+                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    x[8] = c.x; x[9] = c.y; x[10] = c.z; x[11] = c.w;
+                }
+                uint32_t cm;
+                if (dense) cm = filter8<LB, NK, true>(P, x) | (filter8<LB, NK, true>(P, x + 4) << 16);
+                else cm = filter8<LB, NK, false>(P, x) | (filter8<LB, NK, false>(P, x + 4) << 16);
+                if (stage_edge) {                                   // clip to the valid windows
+                    const int lo = min(max((int)sg - (int)lanerel, 0), 32), hi = min(max((int)v_hi - (int)lanerel, 0), 32);
+                    const uint32_t below_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+                    const uint32_t below_lo = lo >= 32 ? 0xFFFFFFFFu : ((1u << lo) - 1u);
+                    cm &= below_hi & ~below_lo;
+                }
+                const bool boundary = (rowrel & (MMG_SUBTILE - 1)) == 0 && rowrel != 0;
+                if (!__any_sync(FULL, cm != 0u)) {
+                    if (boundary) st = close_at(X, st, t0 + (rowrel >> MMG_SUBTILE_SHIFT) - 1u, st.cursor, lane);
+                    continue;
+                }
+                // exclusive prefix of the per-lane candidate counts
+                const uint32_t cnt = __popc(cm);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const uint32_t total = __shfl_sync(FULL, inc, 31);
+                if (boundary) {     // candidates below rowrel + sg still belong to the previous sub-tile
+                    const int bl = min(max((int)(rowrel + sg) - (int)lanerel, 0), 32);
+                    const uint32_t below = bl >= 32 ? 0xFFFFFFFFu : ((1u << bl) - 1u);
+                    const uint32_t nbefore = __reduce_add_sync(FULL, __popc(cm & below));
+                    st = close_at(X, st, t0 + (rowrel >> MMG_SUBTILE_SHIFT) - 1u, st.cursor + nbefore, lane);
+                }
+                if (st.cursor + total <= reg_hi) {                 // otherwise: counted only, the host re-runs with more room
+                    uint32_t *out = X.ev + (st.cursor + inc - cnt);
+                    const uint32_t ws0 = lanerel - sg;              // window start of the lane's bit 0, chunk relative
+                    while (cm) {
+                        const uint32_t b = (uint32_t)__ffs(cm) - 1u;
+                        cm &= cm - 1u;
+                        const uint32_t ca = sa + 16u + b;                       // current element of comparison 0
+                        const int dd = (int)lds8(ca) - (int)lds8(ca - LB);
+                        const uint32_t ws = ws0 + b;
+                        uint32_t res;
+                        if ((((uint32_t)(dd - ev_ed0)) & ev_pmask) != 0u) {
+                            res = lds8(tab0_a + dd);
+                        } else if (ev_nc == 1) {
+                            res = ev_match;
+                        } else {
+                            const int wrel = (int)ws - (int)rel_stage;          // the window usually lies in this stage's buffer
+                            if (wrel >= -16 && wrel + ev_L <= (int)stage_fill) {
+                                const int d1 = (int)lds8(ca - ev_o1c) - (int)lds8(ca - ev_o1p);
+                                if ((((uint32_t)(d1 - ev_ed1)) & ev_pmask) != 0u) res = lds8(tab1_a + d1);
+                                else if (ev_nc == 2) res = ev_match;
+                                else res = eval_window_lds8(stage_a + 16u + (uint32_t)wrel, sprog_a, 2, ev_pmask);
+                            } else {
+                                res = eval_window<1, false>(P, chunk_base + ws);
+                            }
+                        }
+                        *out++ = (ws & (MMG_SUBTILE - 1)) | (res << 16);       // 0x100 << 16 == MMG_EV_MATCH
+                    }
+                }
+                st.cursor += total;
+                stage_cands += total;
+            }
             __syncwarp();
-            st = close_until(X, st, t1, lane);
+            if (lane == 0 && k + MMG_NSTAGES < nst)
+                issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
+                            ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
+            if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
+            // candidate-dense data (low entropy): run the next 15 stages with the depth-2 refinement, then probe again
+            if (dense_left) dense_left--;
+            else if (d2ok && stage_cands >= 96u) dense_left = 15;
         }
+        // the row at chunk-relative 4096 * (t1 - t0) closed the last sub-tile unless the data ended before it
+        if (st.open_t < t1) st = close_at(X, st, st.open_t, st.cursor, lane);
     }
     if (lane == 0) {
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
@@ -1130,24 +1234,25 @@ cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint
 
 #include "launch.h"
 
-// NK (compile-time key count) per width: 8-bit unrolls up to 8 keys, 16-bit fuses the single-key case.
+// NK (compile-time key count): the 8-bit filter unrolls up to 8 keys (lags up to 4 bytes), 16-bit fuses the single-key case.
 template <int W, int LB, bool BE>
 static const void *filter_for_keys(int nkeys) {
-    if (LB == 0) return (const void *)k_filter<W, LB, BE, 0>;
-    if (W == 1) {
-        if (LB > 4) return (const void *)k_filter<W, LB, BE, 0>;      // long wildcard gaps: run-time key loop only
+    if (W == 1 && LB != 0) {
+        constexpr int L8 = LB ? LB : 1;
+        if (LB > 4) return (const void *)k_filter8<L8, 0>;      // long wildcard gaps: run-time key loop only
         switch (nkeys) {
-            case 1: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 1>;
-            case 2: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 2>;
-            case 3: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 3>;
-            case 4: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 4>;
-            case 5: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 5>;
-            case 6: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 6>;
-            case 7: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 7>;
-            case 8: return (const void *)k_filter<W, (LB > 4 ? 1 : LB), BE, 8>;
-            default: return (const void *)k_filter<W, LB, BE, 0>;
+            case 1: return (const void *)k_filter8<L8, 1>;
+            case 2: return (const void *)k_filter8<L8, 2>;
+            case 3: return (const void *)k_filter8<L8, 3>;
+            case 4: return (const void *)k_filter8<L8, 4>;
+            case 5: return (const void *)k_filter8<L8, 5>;
+            case 6: return (const void *)k_filter8<L8, 6>;
+            case 7: return (const void *)k_filter8<L8, 7>;
+            case 8: return (const void *)k_filter8<L8, 8>;
+            default: return (const void *)k_filter8<L8, 0>;
         }
     }
+    if (LB == 0) return (const void *)k_filter<W, LB, BE, 0>;
     return nkeys == 1 ? (const void *)k_filter<W, LB, BE, 1> : (const void *)k_filter<W, LB, BE, 0>;
 }
 
