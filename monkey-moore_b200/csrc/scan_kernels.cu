@@ -900,16 +900,23 @@ __device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom 
 }
 
 #define RESOLVE_THREADS 128
+#define RESOLVE_FAST_J 16u
 
 template <int W, bool BE>
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
           uint64_t *out_off, uint32_t *out_val, uint64_t capacity, uint32_t jp) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
-    // shared: maps [128][npads][jp] | entry phases [128][2] | has flags [128][2] | scalars
+    // shared: maps [128][npads][jp] bytes (general) or words [npads][16][128] (fast) | entry phases [128][2] | has flags [128][2]
     const uint32_t npads = G.npads;
+    // Fast maps: when no advance exceeds J0 (simple / value-scan patterns) a chain that leaves an event lands on a
+    // lattice residue and cannot meet an event of that residue inside the gap it jumps over, so ONE right-to-left
+    // pass over the events yields, per residue r, the exit phase and the number of matches visited by a chain that
+    // sits on residue r in front of the events seen so far:  E[r] <- E[(r + advance) mod J0] (+1 for a match).
+    const bool fast = P.J0 == P.Jmax && P.Jmax <= RESOLVE_FAST_J;
     uint8_t *s_map = rs_smem;
-    uint8_t *s_ph = s_map + (size_t)RESOLVE_THREADS * npads * jp;
+    uint32_t *s_E = reinterpret_cast<uint32_t *>(rs_smem);      // word = exit phase | matches << 8, index (c * 16 + r) * 128 + tid
+    uint8_t *s_ph = s_map + (fast ? (size_t)RESOLVE_THREADS * npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * npads * jp);
     uint8_t *s_has = s_ph + RESOLVE_THREADS * 2;
     __shared__ uint32_t s_bi, s_cnt[RESOLVE_THREADS / 32], s_phase[2];
     __shared__ uint64_t s_before;
@@ -923,6 +930,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const bool bad = events_overflowed(X);
     const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
+    const uint32_t magic = 65536u / J0 + 1u;      // q mod J0 = q - J0 * ((q * magic) >> 16), exact for q < 4096, J0 <= 16
     uint32_t total = 0;       // matches of this block (valid in every thread after the loop)
 
     for (uint32_t tb = t_begin; tb < t_end && !bad; tb += RESOLVE_THREADS) {
@@ -938,7 +946,27 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         uint32_t n = 0;
         uint32_t *ev = nullptr;
         s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0;
-        if (he) {
+        if (he && fast) {
+            n = X.sub_count[t];
+            ev = X.ev + X.sub_start[t];
+            const uint32_t base = NP % J0;
+            for (uint32_t c = 0; c < npads; c++)
+                for (uint32_t r = 0; r < J0; r++)      // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0
+                    s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] = r >= base ? r - base : r + J0 - base;
+            uint32_t seen = 0;
+            for (uint32_t i = n; i-- > 0;) {
+                const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                const uint32_t c = (W == 2) ? (off & 1u) : 0u;
+                const uint32_t q = off / W;
+                const uint32_t r = q - J0 * ((q * magic) >> 16);
+                uint32_t ry = r + MMG_EV_JUMP(w);       // advance <= J0
+                if (ry >= J0) ry -= J0;
+                s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] =
+                    s_E[(c * RESOLVE_FAST_J + ry) * RESOLVE_THREADS + tid] + ((w >> 16) & 0x100u);
+                seen |= 1u << c;
+            }
+            s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
+        } else if (he) {
             n = X.sub_count[t];
             ev = X.ev + X.sub_start[t];
             for (uint32_t c = 0; c < npads; c++) {
@@ -974,7 +1002,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     m &= m - 1;
                     if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);
                     if (lane == 0) s_ph[l * 2 + c] = (uint8_t)ph;
-                    ph = s_map[((size_t)l * npads + c) * jp + ph];
+                    ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * RESOLVE_THREADS + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
                     done = l + 1;
                 }
             }
@@ -984,7 +1012,30 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         __syncthreads();
         // (c) replay the true chains through this thread's events
         uint32_t cnt = 0;
-        if (he) {
+        if (he && fast) {
+            // the match count of the chain that really enters is already known; the replay only marks its matches
+            uint32_t xc[2] = {0u, 0u}, xm[2] = {0u, 0u};
+            for (uint32_t c = 0; c < npads; c++)
+                if (s_has[tid * 2 + c]) {
+                    xc[c] = xm[c] = s_ph[tid * 2 + c];      // entry phase < J0: position and residue coincide
+                    cnt += s_E[(c * RESOLVE_FAST_J + xc[c]) * RESOLVE_THREADS + tid] >> 8;
+                }
+            if (cnt) {
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                    const uint32_t c = (W == 2) ? (off & 1u) : 0u;
+                    const uint32_t q = off / W;
+                    const uint32_t r = q - J0 * ((q * magic) >> 16);
+                    if (xc[c] <= q && r == xm[c]) {
+                        if (w & MMG_EV_MATCH) ev[i] = w | MMG_EV_VISITED;
+                        const uint32_t j = MMG_EV_JUMP(w);
+                        xc[c] = q + j;
+                        xm[c] = r + j >= J0 ? r + j - J0 : r + j;
+                    }
+                }
+            }
+            X.mcount[t] = cnt;
+        } else if (he) {
             uint32_t xc[2] = {s_has[tid * 2] ? s_ph[tid * 2] : 0u, s_has[tid * 2 + 1] ? s_ph[tid * 2 + 1] : 0u};
             for (uint32_t i = 0; i < n; i++) {
                 const uint32_t w = ev[i], off = MMG_EV_OFF(w);
@@ -1312,7 +1363,9 @@ cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgS
                                uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
     const unsigned grid = G.nblocks;                 // one CTA per engine block
     const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
-    const size_t smem = (size_t)RESOLVE_THREADS * G.npads * jp + RESOLVE_THREADS * 4;
+    const bool fast = P.J0 == P.Jmax && (uint32_t)P.Jmax <= RESOLVE_FAST_J;
+    const size_t smem = (fast ? (size_t)RESOLVE_THREADS * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
+                        RESOLVE_THREADS * 4;
     if (P.W == 1) k_resolve<1, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     else if (G.big_endian) k_resolve<2, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     else k_resolve<2, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
