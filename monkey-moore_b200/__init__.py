@@ -20,7 +20,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmoore_b200.so")
+LIB_PATH = os.environ.get("MMG_LIB", os.path.join(_HERE, "libmmoore_b200.so"))   # MMG_LIB: development builds
 
 MMG_OK = 0
 ERROR_NAMES = {1: "Skip table index out of bounds", 2: "empty keyword", 3: "pattern never advances",

@@ -140,11 +140,11 @@ __device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t 
     D[5] = diff_at<LB, 24>(E, O); D[6] = diff_at<LB, 25>(E, O); D[7] = diff_at<LB, 28>(E, O); D[8] = diff_at<LB, 29>(E, O);
     if (DEPTH2) D[0] = diff_at<LB, 13>(E, O);
     const int nk = NK > 0 ? NK : P.nkeys;
-    uint32_t c[9];          // zero half <=> candidate
+    uint32_t c[9];          // per half: 0 <=> candidate, else 1 (the min-accumulation starts from 1)
     if (!DEPTH2) {
         const uint32_t k0 = P.keys[0];
 #pragma unroll
-        for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], k0, 0xFFFFFFFFu);      // per-half add: no carry across
+        for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], k0, 0x00010001u);      // per-half add; halves stay in {0, 1}
         if (NK > 0) {
 #pragma unroll
             for (int j = 1; j < NK; j++) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t 
         uint32_t ap[9], ao[9];      // pass key / the other keys
         const uint32_t k0 = P.keys[0];
 #pragma unroll
-        for (int k = 0; k < 9; k++) { ap[k] = __viaddmin_u16x2(D[k], k0, 0xFFFFFFFFu); ao[k] = 0xFFFFFFFFu; }
+        for (int k = 0; k < 9; k++) { ap[k] = __viaddmin_u16x2(D[k], k0, 0x00010001u); ao[k] = 0x00010001u; }
         if (NK > 0) {
 #pragma unroll
             for (int j = 1; j < NK; j++) {
@@ -194,12 +194,12 @@ __device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t 
             c[2 * q + 2] = NK == 1 ? po : __vminu2(ao[2 * q + 2], po);
         }
     }
-    // halves -> bits: a non-candidate half becomes 1, weighted so that bit e (and 14 + e for the upper halves) names element e
+    // halves (0: candidate, 1: not) -> bits, weighted so that bit e (and 14 + e for the upper halves) names element e
     uint32_t m = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        m += __vminu2(c[2 * q + 1], 0x00010001u) << (4 * q);
-        m += __vminu2(c[2 * q + 2], 0x00010001u) << (4 * q + 1);
+        m += c[2 * q + 1] << (4 * q);
+        m += c[2 * q + 2] << (4 * q + 1);
     }
     return ((m | (m >> 14)) & 0xFFFFu) ^ 0xFFFFu;
 }
@@ -294,6 +294,10 @@ struct SProg {
     uint8_t tab8[512];      // 8-bit searches: skip for every possible difference d, indexed d + 255
     uint8_t tab0[512];      // ditto with the cap of comparison 0 applied: the advance when comparison 0 fails on d
     uint8_t tab1[512];      // ditto for comparison 1
+    // scalars of the 8-bit candidate evaluation (read once per thread with volatile loads: they then live in
+    // registers instead of being re-derived from the kernel parameters inside the hot loop)
+    uint32_t sg, pmask, o1c, o1p, matchword;
+    int32_t ed0, ed1, L;
 };
 __shared__ SProg g_sprog;
 
@@ -301,6 +305,12 @@ __device__ __forceinline__ void load_sprog(const MmgProgram &P) {
     if (threadIdx.x == 0) {
         g_sprog.ncheck = P.ncheck; g_sprog.ntab = P.ntab; g_sprog.tab_default = P.tab_default;
         g_sprog.match_jump = P.match_jump; g_sprog.J0 = P.J0; g_sprog.modular = P.modular;
+        g_sprog.sg = (uint32_t)P.chk[0].i * (uint32_t)P.W;
+        g_sprog.pmask = P.modular ? (P.W == 1 ? 0xFFu : 0xFFFFu) : 0xFFFFFFFFu;
+        g_sprog.o1c = (uint32_t)(P.chk[0].i - P.chk[1].i);
+        g_sprog.o1p = (uint32_t)(P.chk[0].i - P.chk[1].i + P.chk[1].lag);
+        g_sprog.matchword = 0x100u | (uint32_t)P.match_jump;
+        g_sprog.ed0 = P.chk[0].ed; g_sprog.ed1 = P.chk[1].ed; g_sprog.L = P.L;
     }
     for (int i = threadIdx.x; i < P.ncheck; i += blockDim.x) {
         g_sprog.ci[i] = P.chk[i].i; g_sprog.clag[i] = P.chk[i].lag; g_sprog.ced[i] = P.chk[i].ed; g_sprog.ccap[i] = P.chk[i].cap;
@@ -675,19 +685,23 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
 // ------------------------------------------------------------------------------------------
 
 #define MMG_ROW8 1024u
+#define MMG_WARP_SMEM8 ((MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_NSTAGES * 8u + 15u) & ~15u)     // ring + mbarriers, no queue
+#ifndef MMG_FILTER8_MIN_CTAS
+#define MMG_FILTER8_MIN_CTAS 3
+#endif
 
 template <int LB, int NK>
-__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER_MIN_CTAS)
+__global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER8_MIN_CTAS)
 k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t warp = blockIdx.x * MMG_FILTER_WARPS + wib;
     const uint32_t reg_lo = warp * X.ev_per_warp, reg_hi = reg_lo + X.ev_per_warp;
 
-    uint8_t *ring = smem_raw + (size_t)wib * MMG_WARP_SMEM;
+    uint8_t *ring = smem_raw + (size_t)wib * MMG_WARP_SMEM8;
     const uint32_t ring_a = smem_u32(ring);
-    const uint32_t bar_a = ring_a + MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 4u;
+    const uint32_t bar_a = ring_a + MMG_NSTAGES * MMG_STAGE_STRIDE;
     if (lane == 0) {
         for (int i = 0; i < MMG_NSTAGES; i++) mbar_init(bar_a + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -695,15 +709,13 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
 
-    // constants of the exact evaluation, pinned in registers (the empty asm keeps ptxas from re-deriving them per use)
-    uint32_t sg = (uint32_t)P.chk[0].i;                  // window start = position of comparison 0's current element - sg
-    int ev_ed0 = P.chk[0].ed, ev_ed1 = P.chk[1].ed;
-    const int ev_L = P.L, ev_nc = P.ncheck;
-    uint32_t ev_pmask = P.modular ? 0xFFu : 0xFFFFFFFFu;
-    const uint32_t ev_o1c = (uint32_t)(P.chk[0].i - P.chk[1].i), ev_o1p = ev_o1c + (uint32_t)P.chk[1].lag;
-    const uint32_t ev_match = 0x100u | (uint32_t)P.match_jump;
-    uint32_t sprog_a = smem_u32(&g_sprog);
-    asm volatile("" : "+r"(sprog_a), "+r"(sg), "+r"(ev_ed0), "+r"(ev_pmask), "+r"(lane));
+    // constants of the exact evaluation (volatile shared loads: see SProg)
+    const volatile SProg &VP = g_sprog;
+    const uint32_t sg = VP.sg;                            // window start = position of comparison 0's current element - sg
+    const int ev_ed0 = VP.ed0, ev_ed1 = VP.ed1, ev_L = VP.L;
+    const int ev_nc = P.ncheck;
+    const uint32_t ev_pmask = VP.pmask, ev_o1c = VP.o1c, ev_o1p = VP.o1p, ev_match = VP.matchword;
+    const uint32_t sprog_a = smem_u32(&g_sprog);
     const uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
     const uint32_t lt = (1u << lane) - 1u;
     const bool d2ok = P.d2ok != 0;
@@ -764,6 +776,12 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             // bytes of this stage that the bulk copy filled (exact evaluation from shared memory stays inside them)
             const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE_BYTES, copy_end_rel - rel_stage) : 0u;
             const uint32_t stage_a = ring_a + slot * MMG_STAGE_STRIDE;
+            // a candidate whose current element sits at shared address ca has its whole window in this stage's buffer
+            // (halo included) iff  win_lo <= ca <= win_lo + win_span
+            const uint32_t win_lo = stage_a + sg;
+            const int win_span_i = 16 + (int)stage_fill - ev_L;
+            const uint32_t win_span = win_span_i > 0 ? (uint32_t)win_span_i : 0u;
+            const bool win_ok = win_span_i >= 0;
             const bool stage_edge = rel_stage < sg || rel_stage + MMG_STAGE_BYTES > v_hi;
             const bool dense = dense_left != 0;
             const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW8, (len - rel_stage + MMG_ROW8 - 1) / MMG_ROW8);
@@ -797,10 +815,9 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 const uint32_t cnt = __popc(cm);
                 uint32_t inc = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, inc, o);
-                    if (lane >= o) inc += t;
-                }
+                for (int o = 1; o < 32; o <<= 1)
+                    asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }"
+                                 : "+r"(inc) : "r"(o));
                 const uint32_t total = __shfl_sync(FULL, inc, 31);
                 if (boundary) {     // candidates below rowrel + sg still belong to the previous sub-tile
                     const int bl = min(max((int)(rowrel + sg) - (int)lanerel, 0), 32);
@@ -823,12 +840,11 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                         } else if (ev_nc == 1) {
                             res = ev_match;
                         } else {
-                            const int wrel = (int)ws - (int)rel_stage;          // the window usually lies in this stage's buffer
-                            if (wrel >= -16 && wrel + ev_L <= (int)stage_fill) {
+                            if (win_ok && ca - win_lo <= win_span) {          // the window usually lies in this stage's buffer
                                 const int d1 = (int)lds8(ca - ev_o1c) - (int)lds8(ca - ev_o1p);
                                 if ((((uint32_t)(d1 - ev_ed1)) & ev_pmask) != 0u) res = lds8(tab1_a + d1);
                                 else if (ev_nc == 2) res = ev_match;
-                                else res = eval_window_lds8(stage_a + 16u + (uint32_t)wrel, sprog_a, 2, ev_pmask);
+                                else res = eval_window_lds8(ca - sg, sprog_a, 2, ev_pmask);
                             } else {
                                 res = eval_window<1, false>(P, chunk_base + ws);
                             }
@@ -1330,6 +1346,10 @@ static const void *filter_kernel(int W, int lag_bytes, bool be, int nkeys) {
     return fn;
 }
 
+static size_t filter_smem(int W, int lag_bytes) {
+    return (size_t)MMG_FILTER_WARPS * ((W == 1 && lag_bytes != 0) ? MMG_WARP_SMEM8 : MMG_WARP_SMEM);
+}
+
 bool mmg_filter_supported(int W, int lag_bytes) { return filter_kernel(W, lag_bytes, false, 1) != nullptr; }
 
 cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *blocks_per_sm) {
@@ -1343,10 +1363,9 @@ cudaError_t mmg_filter_occupancy(int W, int lag_bytes, bool be, int nkeys, int *
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find({dev, fn});
     if (it != cache.end()) { *blocks_per_sm = it->second; return cudaSuccess; }
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MMG_FILTER_WARPS * MMG_WARP_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem(W, lag_bytes));
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, MMG_FILTER_WARPS * 32,
-                                                      MMG_FILTER_WARPS * MMG_WARP_SMEM);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, MMG_FILTER_WARPS * 32, filter_smem(W, lag_bytes));
     if (e == cudaSuccess) cache[{dev, fn}] = *blocks_per_sm;
     return e;
 }
@@ -1356,7 +1375,7 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
     const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0, P.nkeys);
     if (!fn) return cudaErrorInvalidValue;
     void *args[] = {(void *)&P, (void *)&G, (void *)&X};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, MMG_FILTER_WARPS * MMG_WARP_SMEM, stream);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, filter_smem(P.W, lag_bytes), stream);
 }
 
 cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
