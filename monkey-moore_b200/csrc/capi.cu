@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -41,16 +42,31 @@ int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everythi
 thread_local cudaStream_t g_user_stream = nullptr;   // set by mmg_set_stream: scans run on the caller's stream
 thread_local bool g_use_user_stream = false;
 
+// Per (host thread, device) scan workspace, reused by every tiled scan: nothing is allocated, zeroed or copied per
+// scan in the steady state.  `zero` holds the state that must be all-zero when a scan starts (status words, tickets,
+// look-back words); the resolve kernel restores it when it ends.  Scans on one stream execute in order, so sharing the
+// workspace between scans that are enqueued back to back is safe; `generation` tells a pending scan whether its
+// scratch contents (needed only for the exact re-emission) are still there.
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    uint8_t *zero = nullptr;     size_t zero_bytes = 0;
+    uint8_t *scratch = nullptr;  size_t scratch_bytes = 0;
+    uint32_t *ev = nullptr;      size_t ev_entries = 0;
+    uint64_t generation = 0;
+    bool dirty = false;          // a failed enqueue may have left the zero state non-zero
+};
+
 struct DeviceInfo {
     int device = -1;
     int sms = 0;
     cudaStream_t stream = nullptr;       // the stream scans run on
     cudaStream_t own_stream = nullptr;   // this library's non-blocking stream
+    Workspace ws;
 };
 
 // one stream per host thread and device
 DeviceInfo &device_info() {
-    thread_local std::vector<DeviceInfo> infos;
+    thread_local std::deque<DeviceInfo> infos;      // deque: pending scans keep pointers to their workspace
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) throw ScanError{fail(MMG_ERR_CUDA, "no usable CUDA device")};
     for (auto &d : infos)
@@ -102,13 +118,13 @@ struct TiledState {
     MmgScratch X{};
     int lag_bytes = 0, grid = 0;
     uint64_t total_warps = 0, per_warp = 0, cap = 0;
-    uint8_t *base = nullptr;
-    size_t zero_bytes = 0;
+    uint64_t generation = 0;      // workspace generation of this scan's last enqueue
+    Workspace *ws = nullptr;
 };
 
 struct mmg_results {
     uint64_t count = 0;
-    uint64_t *d_off = nullptr;
+    uint64_t *d_off = nullptr;    // one allocation: offsets, then values
     uint32_t *d_val = nullptr;
     cudaStream_t stream = nullptr;
     mmg_scan_stats stats{};
@@ -119,7 +135,7 @@ struct mmg_results {
     ScanRequest rq{};
     TiledState t;
     Arena *arena = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, after H2D, after filter, end, before filter
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start (host input only), scan start, after filter, end
     uint64_t *status_host = nullptr;                            // pinned slot receiving X.status
     uint32_t launches = 0;
 };
@@ -145,7 +161,7 @@ uint64_t *take_slot() {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
     if (g_slot_pool.empty()) {
         uint64_t *block = nullptr;
-        CU(cudaHostAlloc((void **)&block, 64 * 8 * sizeof(uint64_t), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void **)&block, 64 * 8 * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));   // the resolve kernel writes the status words here
         for (int i = 0; i < 64; i++) g_slot_pool.push_back(block + 8 * i);
     }
     uint64_t *s = g_slot_pool.back();
@@ -159,6 +175,20 @@ void release_inflight(mmg_results *r) {
     if (r->status_host) { g_slot_pool.push_back(r->status_host); r->status_host = nullptr; }
     delete r->arena;
     r->arena = nullptr;
+}
+
+void alloc_results(mmg_results *res, uint64_t cap) {
+    const size_t off_bytes = (cap * sizeof(uint64_t) + 255) & ~(size_t)255;
+    uint8_t *buf = nullptr;
+    CU(cudaMallocAsync((void **)&buf, off_bytes + cap * sizeof(uint32_t), res->stream));
+    res->d_off = reinterpret_cast<uint64_t *>(buf);
+    res->d_val = reinterpret_cast<uint32_t *>(buf + off_bytes);
+}
+
+void free_results(mmg_results *res) {
+    if (res->d_off) cudaFreeAsync(res->d_off, res->stream);
+    res->d_off = nullptr;
+    res->d_val = nullptr;
 }
 
 void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_results *res, uint32_t &launches) {
@@ -182,8 +212,7 @@ void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_r
     CU(cudaStreamSynchronize(stream));
     res->count = total;
     if (total == 0) return;
-    CU(cudaMallocAsync((void **)&res->d_off, total * sizeof(uint64_t), stream));
-    CU(cudaMallocAsync((void **)&res->d_val, total * sizeof(uint32_t), stream));
+    alloc_results(res, total);
     if (rq.npads == 1) {
         CU(mmg_launch_generic_walk(P, G, counts, bases, res->d_off, res->d_val, stream));
         launches += 1;
@@ -196,27 +225,74 @@ void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_r
     }
 }
 
-// enqueues one attempt of the tiled pipeline: zero scratch, filter, maps, phases+walk, scan+emit, status D2H
-void enqueue_tiled(mmg_results *res, bool record_filter_event) {
+template <class T> void grow(T *&ptr, size_t &have, size_t need, cudaStream_t stream, bool zero) {
+    if (need <= have) return;
+    if (ptr) CU(cudaFreeAsync(ptr, stream));
+    ptr = nullptr; have = 0;
+    const size_t want = need + need / 4;
+    CU(cudaMallocAsync((void **)&ptr, want * sizeof(T), stream));
+    have = want;
+    if (zero) CU(cudaMemsetAsync(ptr, 0, want * sizeof(T), stream));
+}
+
+// enqueues one attempt of the tiled pipeline on the thread's workspace: filter, resolve -- nothing else
+void enqueue_tiled(mmg_results *res) {
     const MmgProgram &P = res->rq.prog->dev;
     TiledState &t = res->t;
+    Workspace &ws = *t.ws;
     cudaStream_t stream = res->stream;
-    t.X.ev_per_warp = (uint32_t)t.per_warp;
-    t.X.ev = res->arena->get<uint32_t>(t.per_warp * t.total_warps);
-    CU(cudaMemsetAsync(t.base, 0, t.zero_bytes, stream));
-    if (record_filter_event) CU(cudaEventRecord(res->ev[4], stream));
-    CU(mmg_launch_filter(P, t.G, t.X, t.lag_bytes, t.grid, stream));
-    if (record_filter_event) CU(cudaEventRecord(res->ev[2], stream));
-    CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
+    if (ws.stream != stream) {                    // the caller switched streams: order the workspace's users by hand
+        if (ws.stream) CU(cudaStreamSynchronize(ws.stream));
+        ws.stream = stream;
+    }
+    const MmgGeom &G = t.G;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
+    // zero state
+    const size_t o_status = carve(4 * sizeof(uint64_t));
+    const size_t o_ticket = carve(2 * sizeof(uint32_t));
+    const size_t o_lookback = carve((size_t)G.nblocks * sizeof(uint64_t));
+    const size_t zero_need = off;
+    off = 0;
+    const size_t o_hasev = carve((size_t)G.nsub);
+    const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
+    const size_t scratch_need = off;
+    const bool zero_grew = zero_need > ws.zero_bytes;
+    grow(ws.zero, ws.zero_bytes, zero_need, stream, true);
+    if (ws.dirty && !zero_grew) CU(cudaMemsetAsync(ws.zero, 0, ws.zero_bytes, stream));
+    ws.dirty = true;                              // until both kernels are enqueued
+    grow(ws.scratch, ws.scratch_bytes, scratch_need, stream, false);
+    grow(ws.ev, ws.ev_entries, (size_t)(t.per_warp * t.total_warps), stream, false);
+
+    MmgScratch &X = t.X;
+    X.status = reinterpret_cast<uint64_t *>(ws.zero + o_status);
+    X.ticket = reinterpret_cast<uint32_t *>(ws.zero + o_ticket);
+    X.lookback = reinterpret_cast<uint64_t *>(ws.zero + o_lookback);
+    X.hasev = ws.scratch + o_hasev;
+    X.sub_start = reinterpret_cast<uint32_t *>(ws.scratch + o_start);
+    X.sub_count = reinterpret_cast<uint32_t *>(ws.scratch + o_count);
+    X.mcount = reinterpret_cast<uint32_t *>(ws.scratch + o_mcount);
+    X.mbase = reinterpret_cast<uint64_t *>(ws.scratch + o_mbase);
+    X.ev = ws.ev;
+    X.ev_per_warp = (uint32_t)t.per_warp;
+    X.host_status = res->status_host;             // pinned + mapped: same address on the device (UVA)
+
+    CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
+    if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
+    CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
+    ws.dirty = false;
     res->launches += 2;
-    CU(cudaMemcpyAsync(res->status_host, t.X.status, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    t.generation = ++ws.generation;
 }
 
 void launch_tiled(mmg_results *res, DeviceInfo &dev) {
     const ScanRequest &rq = res->rq;
     const MmgProgram &P = rq.prog->dev;
     TiledState &t = res->t;
-    Arena &arena = *res->arena;
+    t.ws = &dev.ws;
     const int W = P.W;
     t.lag_bytes = (P.ncheck > 0 && P.nkeys >= 0) ? P.chk[0].lag * W : 0;
     if (!mmg_filter_supported(W, t.lag_bytes) || g_path_override == 2) t.lag_bytes = 0;   // evaluate every window exactly
@@ -243,41 +319,16 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev) {
     G.chunk_subs = cs;
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
 
-    MmgScratch &X = t.X;
-    // one allocation for all per-scan scratch; the zero-initialised part comes first
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
-    const size_t o_status = carve(4 * sizeof(uint64_t));
-    const size_t o_ticket = carve(sizeof(uint32_t));
-    const size_t o_lookback = carve((size_t)G.nblocks * sizeof(uint64_t));
-    const size_t o_hasev = carve((size_t)G.nsub);
-    t.zero_bytes = off;
-    const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
-    uint8_t *base = arena.get<uint8_t>(off);
-    t.base = base;
-    X.status = reinterpret_cast<uint64_t *>(base + o_status);
-    X.ticket = reinterpret_cast<uint32_t *>(base + o_ticket);
-    X.lookback = reinterpret_cast<uint64_t *>(base + o_lookback);
-    X.hasev = base + o_hasev;
-    X.sub_start = reinterpret_cast<uint32_t *>(base + o_start);
-    X.sub_count = reinterpret_cast<uint32_t *>(base + o_count);
-    X.mcount = reinterpret_cast<uint32_t *>(base + o_mcount);
-    X.mbase = reinterpret_cast<uint64_t *>(base + o_mbase);
-
     // optimistic result capacity: what this pattern produced last time plus slack
     t.cap = std::max<uint64_t>(4096, rq.prog->last_count + rq.prog->last_count / 4 + 1024);
-    CU(cudaMallocAsync((void **)&res->d_off, t.cap * sizeof(uint64_t), res->stream));
-    CU(cudaMallocAsync((void **)&res->d_val, t.cap * sizeof(uint32_t), res->stream));
+    alloc_results(res, t.cap);
 
     // event capacity: private, equally sized regions per filter warp; grown and re-run on overflow
     t.per_warp = std::max<uint64_t>(256, rq.S / 8 / t.total_warps);
     if (rq.prog->last_events_per_warp) t.per_warp = std::max<uint64_t>(256, rq.prog->last_events_per_warp * 2);
     if (t.lag_bytes == 0) t.per_warp = std::max<uint64_t>(t.per_warp, (rq.S / t.total_warps + MMG_SUBTILE) * 2);
     if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
-    enqueue_tiled(res, true);
+    enqueue_tiled(res);
 }
 
 // completes a tiled scan: waits, re-runs with exact sizes when an optimistic buffer was too small
@@ -286,12 +337,12 @@ void finish_tiled(mmg_results *res) {
     TiledState &t = res->t;
     cudaStream_t stream = res->stream;
     CU(cudaEventSynchronize(res->ev[3]));
-    uint64_t *status = res->status_host;
+    volatile uint64_t *status = res->status_host;
     for (int attempt = 0; status[0] > t.per_warp; attempt++) {
         if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
         t.per_warp = status[0] + status[0] / 4 + 64;
         if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
-        enqueue_tiled(res, false);
+        enqueue_tiled(res);
         CU(cudaEventRecord(res->ev[3], stream));
         CU(cudaStreamSynchronize(stream));
     }
@@ -300,14 +351,17 @@ void finish_tiled(mmg_results *res) {
     res->stats.events = status[1];
     res->count = status[2];
     if (res->count > t.cap) {
-        // the optimistic buffer was too small: allocate exactly and emit again from the stored bases
-        CU(cudaFreeAsync(res->d_off, stream));
-        CU(cudaFreeAsync(res->d_val, stream));
-        res->d_off = nullptr; res->d_val = nullptr;
-        CU(cudaMallocAsync((void **)&res->d_off, res->count * sizeof(uint64_t), stream));
-        CU(cudaMallocAsync((void **)&res->d_val, res->count * sizeof(uint32_t), stream));
-        CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
-        res->launches += 1;
+        // the optimistic buffer was too small: allocate exactly and emit again from the stored bases -- or, when
+        // another scan has used the workspace since, run the whole scan again
+        free_results(res);
+        t.cap = res->count;
+        alloc_results(res, t.cap);
+        if (t.generation == t.ws->generation) {
+            CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
+            res->launches += 1;
+        } else {
+            enqueue_tiled(res);
+        }
         CU(cudaEventRecord(res->ev[3], stream));
         CU(cudaStreamSynchronize(stream));
     }
@@ -321,8 +375,9 @@ int finish_scan(mmg_results *r) {
         if (r->tiled) finish_tiled(r);
         else CU(cudaEventSynchronize(r->ev[3]));
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1])); r->stats.ms_h2d = r->from_host ? ms : 0.f;
-        CU(cudaEventElapsedTime(&ms, r->tiled ? r->ev[4] : r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
+        r->stats.ms_h2d = 0.f;
+        if (r->from_host) { CU(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1])); r->stats.ms_h2d = ms; }
+        CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
         CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[3])); r->stats.ms_total = ms;
         r->stats.launches = r->launches;
     } catch (const ScanError &e) {
@@ -339,9 +394,8 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
     *out = nullptr;
     mmg_results *res = new mmg_results();
     try {
-        int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-            throw ScanError{fail(MMG_ERR_CUDA, "no CUDA device: this library has no CPU fallback")};
+        static const int ndev = [] { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; } return n; }();
+        if (ndev == 0) throw ScanError{fail(MMG_ERR_CUDA, "no CUDA device: this library has no CPU fallback")};
         DeviceInfo &dev = device_info();
         res->stream = dev.stream;
         res->stats.bytes_scanned = nbytes;
@@ -351,8 +405,8 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         res->arena = new Arena(dev.stream);
         res->from_host = mem == MMG_MEM_HOST;
         const uint8_t *d_bytes = static_cast<const uint8_t *>(bytes);
-        CU(cudaEventRecord(res->ev[0], dev.stream));
         if (mem == MMG_MEM_HOST) {
+            CU(cudaEventRecord(res->ev[0], dev.stream));
             uint8_t *buf = res->arena->get<uint8_t>(nbytes + 16);
             CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, dev.stream));
             d_bytes = buf;
@@ -553,8 +607,7 @@ const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? don
 void mmg_results_free(mmg_results *r) {
     if (!r) return;
     if (r->pending) finish_scan(r);
-    if (r->d_off) cudaFreeAsync(r->d_off, r->stream);
-    if (r->d_val) cudaFreeAsync(r->d_val, r->stream);
+    if (r->d_off) cudaFreeAsync(r->d_off, r->stream);      // one allocation: offsets, then values
     delete r;
 }
 

@@ -270,16 +270,21 @@ struct WarpState {
 };
 
 __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState st, uint32_t t, int lane) {
-    // only sub-tiles that own events are recorded (extent + an entry in the non-empty list)
-    if (st.open_t < t && st.cursor != st.open_start) {
+    // every sub-tile the warp passes gets its has-events flag (the resolve kernel reads it without any zeroing
+    // by the host); extents are recorded only where events exist
+    if (st.open_t < t) {
+        const bool has = st.cursor != st.open_start;
         if (lane == 0) {
-            X.sub_start[st.open_t] = st.open_start;
-            X.sub_count[st.open_t] = st.cursor - st.open_start;
-            X.hasev[st.open_t] = 1;
+            if (has) {
+                X.sub_start[st.open_t] = st.open_start;
+                X.sub_count[st.open_t] = st.cursor - st.open_start;
+            }
+            X.hasev[st.open_t] = has ? 1 : 0;
         }
+        for (uint32_t u = st.open_t + 1 + (uint32_t)lane; u < t; u += 32) X.hasev[u] = 0;      // passed without events
         st.open_start = st.cursor;
+        st.open_t = t;
     }
-    if (st.open_t < t) st.open_t = t;
     return st;
 }
 
@@ -507,10 +512,13 @@ __device__ __noinline__ uint32_t eval_window_lds8(uint32_t wa, uint32_t sp, int 
 
 // record the extent of sub-tile t's event list: [st.open_start, cut)
 __device__ __forceinline__ WarpState close_at(const MmgScratch &X, WarpState st, uint32_t t, uint32_t cut, int lane) {
-    if (lane == 0 && cut != st.open_start) {
-        X.sub_start[t] = st.open_start;
-        X.sub_count[t] = cut - st.open_start;
-        X.hasev[t] = 1;
+    if (lane == 0) {
+        const bool has = cut != st.open_start;
+        if (has) {
+            X.sub_start[t] = st.open_start;
+            X.sub_count[t] = cut - st.open_start;
+        }
+        X.hasev[t] = has ? 1 : 0;       // written for every sub-tile: nothing to zero before a scan
     }
     st.open_start = cut;
     st.open_t = t + 1;
@@ -1110,29 +1118,49 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         }
     }
     __syncthreads();
-    if (total == 0) return;
 
     // (e) ordered emission
-    uint64_t running = s_before;
-    for (uint32_t tb = t_begin; tb < t_end; tb += RESOLVE_THREADS) {
-        const uint32_t t = tb + tid;
-        const bool he = t < t_end && X.hasev[t] != 0;
-        const uint32_t cnt = he ? X.mcount[t] : 0u;
-        uint32_t incl = cnt;
+    if (total != 0) {
+        uint64_t running = s_before;
+        for (uint32_t tb = t_begin; tb < t_end; tb += RESOLVE_THREADS) {
+            const uint32_t t = tb + tid;
+            const bool he = t < t_end && X.hasev[t] != 0;
+            const uint32_t cnt = he ? X.mcount[t] : 0u;
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            __syncthreads();
+            if (lane == 31) s_cnt[wid] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, round_total = 0;
+            for (int i = 0; i < RESOLVE_THREADS / 32; i++) { if (i < wid) wbase += s_cnt[i]; round_total += s_cnt[i]; }
+            const uint64_t at = running + wbase + (incl - cnt);
+            if (he) X.mbase[t] = at;
+            if (cnt && at + cnt <= capacity) emit_subtile<W, BE>(P, G, X, t, at, out_off, out_val);
+            running += round_total;
         }
+    }
+
+    // (f) the last CTA to finish hands the status words to the host (pinned, device-visible slot) and restores the
+    // all-zero state of the workspace, so the next scan on this stream needs no memset and no status copy
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(X.ticket + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < 4) X.host_status[tid] = reinterpret_cast<volatile uint64_t *>(X.status)[tid];
+        __threadfence_system();
         __syncthreads();
-        if (lane == 31) s_cnt[wid] = incl;
-        __syncthreads();
-        uint32_t wbase = 0, round_total = 0;
-        for (int i = 0; i < RESOLVE_THREADS / 32; i++) { if (i < wid) wbase += s_cnt[i]; round_total += s_cnt[i]; }
-        const uint64_t at = running + wbase + (incl - cnt);
-        if (he) X.mbase[t] = at;
-        if (cnt && at + cnt <= capacity) emit_subtile<W, BE>(P, G, X, t, at, out_off, out_val);
-        running += round_total;
+        if (tid < 4) X.status[tid] = 0;
+        if (tid < 2) X.ticket[tid] = 0;
+        for (uint32_t i = tid; i < G.nblocks; i += RESOLVE_THREADS) X.lookback[i] = 0;
     }
 }
 

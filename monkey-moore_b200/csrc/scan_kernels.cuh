@@ -54,15 +54,18 @@ struct MmgGeom {
 struct MmgScratch {
     uint32_t *ev;          // event words, one private region per filter warp
     uint32_t ev_per_warp;
-    uint8_t *hasev;        // [nsub] sub-tile owns events (zeroed by the host, set by the filter)
+    uint8_t *hasev;        // [nsub] sub-tile owns events (written for every sub-tile by the filter)
     uint32_t *sub_start;   // [nsub] first event of the sub-tile (valid where hasev)
     uint32_t *sub_count;   // [nsub] ditto
     uint32_t *mcount;      // [nsub] visited matches (valid where hasev)
     uint64_t *mbase;       // [nsub] position of the sub-tile's first match in the output (valid where hasev)
+    // Zero state: all zero when a scan starts.  The last CTA of the resolve kernel to finish copies `status` to the
+    // host's pinned slot and zeroes it all again, so a workspace serves scan after scan without a memset.
     uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events
-                           // [2] total matches [3] next chunk (dynamic scheduling)   (zeroed by the host)
-    uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts (zeroed by the host)
-    uint32_t *ticket;      // block ticket of the resolve kernel (zeroed by the host)
+                           // [2] total matches [3] next chunk (dynamic scheduling)
+    uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts
+    uint32_t *ticket;      // [0] block ticket of the resolve kernel  [1] CTAs of the resolve kernel that are done
+    uint64_t *host_status; // pinned, device-visible: receives status[0..3] when the resolve kernel ends
 };
 
 #endif
