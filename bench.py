@@ -195,13 +195,14 @@ def run_ours(args, w):
 
     pending_gather = [None]
 
-    def step(collect=None):
-        launches, filt_ms, filt_bytes = 0, 0.0, 0
-        # the searches of a step are independent: enqueue them all, then complete them (the host work of
-        # one overlaps the GPU work of the other)
-        held = [prog.engine_scan(blob, w.block_size, big_endian=s.big_endian, file_size=total_size,
+    def enqueue_step():
+        # the searches of a step are independent: all of them are enqueued at once (no host wait in between)
+        return [prog.engine_scan(blob, w.block_size, big_endian=s.big_endian, file_size=total_size,
                                  first_block=b0, num_blocks=b1 - b0, asynchronous=True)
                 for prog, s in zip(progs, w.searches)]
+
+    def complete_step(held, collect=None):
+        launches, filt_ms, filt_bytes = 0, 0.0, 0
         for res in held:
             st = res.stats()
             launches += st["launches"]
@@ -221,6 +222,9 @@ def run_ours(args, w):
                 r.close()
         return launches, filt_ms, filt_bytes
 
+    def step(collect=None):
+        return complete_step(enqueue_step(), collect)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -238,11 +242,21 @@ def run_ours(args, w):
     barrier()
     e0.record(stream)
     t0 = time.perf_counter()
+    # software pipeline over the steps: step k+1 is enqueued before the host collects step k (counts, statistics,
+    # gather), so the device never waits for the host between steps; every step is complete before e1 / the barrier
+    prev = None
     for _ in range(args.steps):
-        l, fm, fb = step()
-        launches += l
-        filt_ms += fm
-        filt_bytes += fb
+        cur = enqueue_step()
+        if prev is not None:
+            l, fm, fb = complete_step(prev)
+            launches += l
+            filt_ms += fm
+            filt_bytes += fb
+        prev = cur
+    l, fm, fb = complete_step(prev)
+    launches += l
+    filt_ms += fm
+    filt_bytes += fb
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0

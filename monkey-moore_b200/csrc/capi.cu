@@ -56,12 +56,22 @@ struct Workspace {
     bool dirty = false;          // a failed enqueue may have left the zero state non-zero
 };
 
+// Scans run on one of two internal streams ("lanes"), each with its own workspace, ordered after whatever the
+// caller's stream holds when the scan is enqueued.  Consecutive scans therefore overlap: the latency-bound resolve
+// kernel of one runs beside the bandwidth-bound filter of the next, and a host-input copy beside the previous scan.
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr;
+    Workspace ws;
+};
+
 struct DeviceInfo {
     int device = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;       // the stream scans run on
+    cudaStream_t stream = nullptr;       // the caller's stream (mmg_set_stream) or own_stream: scans are ordered after it
     cudaStream_t own_stream = nullptr;   // this library's non-blocking stream
-    Workspace ws;
+    Lane lanes[2];
+    unsigned next_lane = 0;
 };
 
 // one stream per host thread and device
@@ -75,6 +85,10 @@ DeviceInfo &device_info() {
     d.device = dev;
     CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     CU(cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
+    for (Lane &l : d.lanes) {
+        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    }
     d.stream = g_use_user_stream ? g_user_stream : d.own_stream;
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -281,18 +295,19 @@ void enqueue_tiled(mmg_results *res) {
     X.host_status = res->status_host;             // pinned + mapped: same address on the device (UVA)
 
     CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
-    if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
+    static const bool no_filter_event = getenv("MMG_NO_FILTER_EVENT") != nullptr;      // experiment
+    if (res->launches == 0 && !no_filter_event) CU(cudaEventRecord(res->ev[2], stream));
     CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
     ws.dirty = false;
     res->launches += 2;
     t.generation = ++ws.generation;
 }
 
-void launch_tiled(mmg_results *res, DeviceInfo &dev) {
+void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     const ScanRequest &rq = res->rq;
     const MmgProgram &P = rq.prog->dev;
     TiledState &t = res->t;
-    t.ws = &dev.ws;
+    t.ws = &ws;
     const int W = P.W;
     t.lag_bytes = (P.ncheck > 0 && P.nkeys >= 0) ? P.chk[0].lag * W : 0;
     if (!mmg_filter_supported(W, t.lag_bytes) || g_path_override == 2) t.lag_bytes = 0;   // evaluate every window exactly
@@ -377,7 +392,7 @@ int finish_scan(mmg_results *r) {
         float ms = 0;
         r->stats.ms_h2d = 0.f;
         if (r->from_host) { CU(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1])); r->stats.ms_h2d = ms; }
-        CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[2])); r->stats.ms_filter = ms;
+        if (cudaEventElapsedTime(&ms, r->ev[1], r->ev[2]) == cudaSuccess) r->stats.ms_filter = ms; else cudaGetLastError();
         CU(cudaEventElapsedTime(&ms, r->ev[1], r->ev[3])); r->stats.ms_total = ms;
         r->stats.launches = r->launches;
     } catch (const ScanError &e) {
@@ -397,34 +412,38 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         static const int ndev = [] { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; } return n; }();
         if (ndev == 0) throw ScanError{fail(MMG_ERR_CUDA, "no CUDA device: this library has no CPU fallback")};
         DeviceInfo &dev = device_info();
-        res->stream = dev.stream;
+        Lane &lane = dev.lanes[dev.next_lane++ & 1u];
+        cudaStream_t stream = lane.stream;
+        res->stream = stream;
         res->stats.bytes_scanned = nbytes;
         if (nbytes == 0 || nblocks == 0) { *out = res; return MMG_OK; }
+        CU(cudaEventRecord(lane.fork, dev.stream));           // everything the caller enqueued so far (the input!) comes first
+        CU(cudaStreamWaitEvent(stream, lane.fork, 0));
         for (auto &e : res->ev) e = take_event();
         res->status_host = take_slot();
-        res->arena = new Arena(dev.stream);
+        res->arena = new Arena(stream);
         res->from_host = mem == MMG_MEM_HOST;
         const uint8_t *d_bytes = static_cast<const uint8_t *>(bytes);
         if (mem == MMG_MEM_HOST) {
-            CU(cudaEventRecord(res->ev[0], dev.stream));
+            CU(cudaEventRecord(res->ev[0], stream));
             uint8_t *buf = res->arena->get<uint8_t>(nbytes + 16);
-            CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, dev.stream));
+            CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, stream));
             d_bytes = buf;
         } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
             throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
         }
-        CU(cudaEventRecord(res->ev[1], dev.stream));
+        CU(cudaEventRecord(res->ev[1], stream));
         res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
         const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
         res->tiled = regular && g_path_override != 1;
         res->stats.fast_path = res->tiled;
         if (res->tiled) {
-            launch_tiled(res, dev);
+            launch_tiled(res, dev, lane.ws);
         } else {
-            run_generic(res->rq, dev.stream, *res->arena, res, res->launches);
-            CU(cudaEventRecord(res->ev[2], dev.stream));
+            run_generic(res->rq, stream, *res->arena, res, res->launches);
+            CU(cudaEventRecord(res->ev[2], stream));
         }
-        CU(cudaEventRecord(res->ev[3], dev.stream));
+        CU(cudaEventRecord(res->ev[3], stream));
         res->pending = true;
         *out = res;
         return MMG_OK;

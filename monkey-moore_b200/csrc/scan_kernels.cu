@@ -546,6 +546,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
+    asm volatile("griddepcontrol.launch_dependents;");      // the resolve kernel's CTAs may take free SM resources now
 
     WarpState st;
     st.cursor = reg_lo;
@@ -716,6 +717,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
+    asm volatile("griddepcontrol.launch_dependents;");      // the resolve kernel's CTAs may take free SM resources now
 
     // constants of the exact evaluation (volatile shared loads: see SProg)
     const volatile SProg &VP = g_sprog;
@@ -950,7 +952,9 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     if (tid == 0) { s_bi = atomicAdd(X.ticket, 1u); s_phase[0] = 0; s_phase[1] = 0; }
     __syncthreads();
     const uint32_t bi = s_bi;
-    if (bi >= G.nblocks) return;
+    // launched with programmatic stream serialization: everything above overlaps the tail of the filter kernel;
+    // its results (events, flags, status words) are visible only after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool bad = events_overflowed(X);
     const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
@@ -1413,10 +1417,17 @@ cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgS
     const bool fast = P.J0 == P.Jmax && (uint32_t)P.Jmax <= RESOLVE_FAST_J;
     const size_t smem = (fast ? (size_t)RESOLVE_THREADS * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
                         RESOLVE_THREADS * 4;
-    if (P.W == 1) k_resolve<1, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else if (G.big_endian) k_resolve<2, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else k_resolve<2, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    return cudaGetLastError();
+    // programmatic dependent launch: the CTAs become resident while the filter kernel is still running and wait at
+    // griddepcontrol.wait, so launch latency and block scheduling are off the critical path
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RESOLVE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (P.W == 1) return cudaLaunchKernelEx(&cfg, k_resolve<1, false>, P, G, X, out_off, out_val, capacity, jp);
+    if (G.big_endian) return cudaLaunchKernelEx(&cfg, k_resolve<2, true>, P, G, X, out_off, out_val, capacity, jp);
+    return cudaLaunchKernelEx(&cfg, k_resolve<2, false>, P, G, X, out_off, out_val, capacity, jp);
 }
 
 // exclusive scan of n u32 counts into u64 bases; bsum must hold ceil(n/1024) entries; *total receives the sum
