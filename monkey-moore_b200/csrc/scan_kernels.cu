@@ -253,12 +253,14 @@ __device__ __forceinline__ bool prefilter16(const MmgProgram &P, const uint32_t 
 #pragma unroll
         for (int k = 0; k < 8; k++) d[k] = cur[k] - prv[k];
         const int nk = P.nkeys;
-#pragma unroll 1
+        uint32_t a4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};      // four independent min chains
+#pragma unroll 2
         for (int j = 0; j < nk; j++) {
             const uint32_t c = P.pkeys[j];
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc = __viaddmin_u16x2(d[k], c, acc);
+            for (int k = 0; k < 8; k++) a4[k & 3] = __viaddmin_u16x2(d[k], c, a4[k & 3]);
         }
+        acc = __vimin3_u16x2(__vminu2(a4[0], a4[1]), a4[2], a4[3]);
     }
     return ((acc & 0xFFFFu) == 0) || ((acc >> 16) <= 2u);
 }
@@ -441,7 +443,9 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+#ifndef MMG_STAGE_BYTES
 #define MMG_STAGE_BYTES 2048u                       // 4 rows
+#endif
 #define MMG_STAGE_STRIDE (MMG_STAGE_BYTES + 16u)    // + 16-byte left halo
 #ifndef MMG_NSTAGES
 #define MMG_NSTAGES 3
@@ -456,11 +460,12 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 // Stage `k` of a chunk holds the slice bytes [p0 + k*2048 - 16, p0 + (k+1)*2048), clipped to
 // [0, copy_end) where copy_end is the 16-byte-aligned end of what the chunk needs; an unaligned tail
 // of the slice (< 16 bytes) is patched in by the lanes.  All positions are relative to p0 (32 bit).
+template <uint32_t STAGE = MMG_STAGE_BYTES>
 __device__ __forceinline__ void issue_stage(const uint8_t *chunk_base, bool at_slice_start, uint32_t rel_stage,
                                             uint32_t copy_end_rel, uint32_t dst, uint32_t bar) {
     uint32_t skip = 0, lo = rel_stage - 16u;          // rel_stage == 0 && at_slice_start: no left halo exists
     if (rel_stage == 0 && at_slice_start) { skip = 16u; lo = 0; }
-    const uint32_t hi = min(rel_stage + MMG_STAGE_BYTES, copy_end_rel);
+    const uint32_t hi = min(rel_stage + STAGE, copy_end_rel);
     if ((int32_t)(hi - lo) > 0) {
         const uint32_t bytes = hi - lo;
         mbar_expect_tx(bar, bytes);
@@ -694,7 +699,12 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
 // ------------------------------------------------------------------------------------------
 
 #define MMG_ROW8 1024u
-#define MMG_WARP_SMEM8 ((MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_NSTAGES * 8u + 15u) & ~15u)     // ring + mbarriers, no queue
+// the 8-bit kernel runs two 4 KiB stages per warp (same bytes in flight as three 2 KiB stages, half the per-stage
+// bookkeeping per row)
+#define MMG_STAGE8 4096u
+#define MMG_NSTAGES8 2
+#define MMG_STRIDE8 (MMG_STAGE8 + 16u)
+#define MMG_WARP_SMEM8 ((MMG_NSTAGES8 * MMG_STRIDE8 + MMG_NSTAGES8 * 8u + 15u) & ~15u)     // ring + mbarriers, no queue
 #ifndef MMG_FILTER8_MIN_CTAS
 #define MMG_FILTER8_MIN_CTAS 3
 #endif
@@ -710,9 +720,9 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 
     uint8_t *ring = smem_raw + (size_t)wib * MMG_WARP_SMEM8;
     const uint32_t ring_a = smem_u32(ring);
-    const uint32_t bar_a = ring_a + MMG_NSTAGES * MMG_STAGE_STRIDE;
+    const uint32_t bar_a = ring_a + MMG_NSTAGES8 * MMG_STRIDE8;
     if (lane == 0) {
-        for (int i = 0; i < MMG_NSTAGES; i++) mbar_init(bar_a + 8 * i, 1);
+        for (int i = 0; i < MMG_NSTAGES8; i++) mbar_init(bar_a + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -732,7 +742,10 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 
     WarpState st;
     st.cursor = reg_lo;
-    uint32_t dense_left = 0;          // stages the depth-2 refinement stays on before the candidate density is probed again
+    // stages the depth-2 refinement stays on before the candidate density is probed again; with a single key every
+    // candidate is a "comparison 0 passes" window, so the refinement is always worth its cost
+    const bool always_dense = d2ok && (NK == 1 || P.nkeys == 1);
+    uint32_t dense_left = always_dense ? 0xFFFFFFFFu : 0u;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
 
     for (;;) {
@@ -760,7 +773,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         const uint64_t s16 = (G.S + 15) & ~(uint64_t)15;
         const uint64_t p_end = min(p0 + chunk_bytes + sg + 1, s16);
         const uint32_t len = p_end > p0 ? (uint32_t)(p_end - p0) : 0u;            // bytes of position space to process
-        const uint32_t nst = (len + MMG_STAGE_BYTES - 1) / MMG_STAGE_BYTES;
+        const uint32_t nst = (len + MMG_STAGE8 - 1) / MMG_STAGE8;
         const uint64_t aligned_end = G.S & ~(uint64_t)15;
         const uint64_t want_end = min((p_end + 15) & ~(uint64_t)15, aligned_end);
         const uint32_t copy_end_rel = want_end > p0 ? (uint32_t)(want_end - p0) : 0u;
@@ -771,30 +784,30 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 
         if (lane == 0) {
             uint32_t sl = slot;
-            for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
-                issue_stage(chunk_base, at_start, k * MMG_STAGE_BYTES, copy_end_rel, ring_a + sl * MMG_STAGE_STRIDE, bar_a + 8 * sl);
-                sl = sl + 1 == MMG_NSTAGES ? 0 : sl + 1;
+            for (uint32_t k = 0; k < nst && k < MMG_NSTAGES8; k++) {
+                issue_stage<MMG_STAGE8>(chunk_base, at_start, k * MMG_STAGE8, copy_end_rel, ring_a + sl * MMG_STRIDE8, bar_a + 8 * sl);
+                sl = sl + 1 == MMG_NSTAGES8 ? 0 : sl + 1;
             }
         }
-        for (uint32_t k = 0, rel_stage = 0; k < nst; k++, rel_stage += MMG_STAGE_BYTES) {
+        for (uint32_t k = 0, rel_stage = 0; k < nst; k++, rel_stage += MMG_STAGE8) {
             mbar_wait(bar_a + 8 * slot, parity);
-            if (tail_rel - rel_stage < MMG_STAGE_BYTES) {      // patch the last (S mod 16) bytes of the slice
+            if (tail_rel - rel_stage < MMG_STAGE8) {      // patch the last (S mod 16) bytes of the slice
                 if (lane < 16 && aligned_end + lane < G.S)
-                    ring[slot * MMG_STAGE_STRIDE + 16 + (tail_rel - rel_stage) + lane] = G.data[aligned_end + lane];
+                    ring[slot * MMG_STRIDE8 + 16 + (tail_rel - rel_stage) + lane] = G.data[aligned_end + lane];
                 __syncwarp();
             }
             // bytes of this stage that the bulk copy filled (exact evaluation from shared memory stays inside them)
-            const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE_BYTES, copy_end_rel - rel_stage) : 0u;
-            const uint32_t stage_a = ring_a + slot * MMG_STAGE_STRIDE;
+            const uint32_t stage_fill = copy_end_rel > rel_stage ? min(MMG_STAGE8, copy_end_rel - rel_stage) : 0u;
+            const uint32_t stage_a = ring_a + slot * MMG_STRIDE8;
             // a candidate whose current element sits at shared address ca has its whole window in this stage's buffer
             // (halo included) iff  win_lo <= ca <= win_lo + win_span
             const uint32_t win_lo = stage_a + sg;
             const int win_span_i = 16 + (int)stage_fill - ev_L;
             const uint32_t win_span = win_span_i > 0 ? (uint32_t)win_span_i : 0u;
             const bool win_ok = win_span_i >= 0;
-            const bool stage_edge = rel_stage < sg || rel_stage + MMG_STAGE_BYTES > v_hi;
+            const bool stage_edge = rel_stage < sg || rel_stage + MMG_STAGE8 > v_hi;
             const bool dense = dense_left != 0;
-            const uint32_t rows = min(MMG_STAGE_BYTES / MMG_ROW8, (len - rel_stage + MMG_ROW8 - 1) / MMG_ROW8);
+            const uint32_t rows = min(MMG_STAGE8 / MMG_ROW8, (len - rel_stage + MMG_ROW8 - 1) / MMG_ROW8);
             uint32_t stage_cands = 0;
 #pragma unroll 1
             for (uint32_t r = 0; r < rows; r++) {
@@ -866,13 +879,14 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 stage_cands += total;
             }
             __syncwarp();
-            if (lane == 0 && k + MMG_NSTAGES < nst)
-                issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
-                            ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
-            if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
+            if (lane == 0 && k + MMG_NSTAGES8 < nst)
+                issue_stage<MMG_STAGE8>(chunk_base, at_start, rel_stage + MMG_NSTAGES8 * MMG_STAGE8, copy_end_rel,
+                            ring_a + slot * MMG_STRIDE8, bar_a + 8 * slot);
+            if (++slot == MMG_NSTAGES8) { slot = 0; parity ^= 1u; }
             // candidate-dense data (low entropy): run the next 15 stages with the depth-2 refinement, then probe again
-            if (dense_left) dense_left--;
-            else if (d2ok && stage_cands >= 96u) dense_left = 15;
+            if (always_dense) { }
+            else if (dense_left) dense_left--;
+            else if (d2ok && stage_cands >= MMG_STAGE8 * 3u / 64u) dense_left = 15;
         }
         // the row at chunk-relative 4096 * (t1 - t0) closed the last sub-tile unless the data ended before it
         if (st.open_t < t1) st = close_at(X, st, st.open_t, st.cursor, lane);
@@ -982,8 +996,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 for (uint32_t r = 0; r < J0; r++)      // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0
                     s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] = r >= base ? r - base : r + J0 - base;
             uint32_t seen = 0;
-            for (uint32_t i = n; i-- > 0;) {
-                const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+            auto step = [&](uint32_t w) {
+                const uint32_t off = MMG_EV_OFF(w);
                 const uint32_t c = (W == 2) ? (off & 1u) : 0u;
                 const uint32_t q = off / W;
                 const uint32_t r = q - J0 * ((q * magic) >> 16);
@@ -992,7 +1006,16 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] =
                     s_E[(c * RESOLVE_FAST_J + ry) * RESOLVE_THREADS + tid] + ((w >> 16) & 0x100u);
                 seen |= 1u << c;
+            };
+            uint32_t i = n;
+            for (; i >= 8; i -= 8) {        // eight independent loads in flight per thread, then the dependent updates
+                uint32_t w8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) w8[k] = ev[i - 1 - k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) step(w8[k]);
             }
+            while (i-- > 0) step(ev[i]);
             s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
         } else if (he) {
             n = X.sub_count[t];
@@ -1049,8 +1072,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     cnt += s_E[(c * RESOLVE_FAST_J + xc[c]) * RESOLVE_THREADS + tid] >> 8;
                 }
             if (cnt) {
-                for (uint32_t i = 0; i < n; i++) {
-                    const uint32_t w = ev[i], off = MMG_EV_OFF(w);
+                auto visit = [&](uint32_t i, uint32_t w) {
+                    const uint32_t off = MMG_EV_OFF(w);
                     const uint32_t c = (W == 2) ? (off & 1u) : 0u;
                     const uint32_t q = off / W;
                     const uint32_t r = q - J0 * ((q * magic) >> 16);
@@ -1060,7 +1083,16 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                         xc[c] = q + j;
                         xm[c] = r + j >= J0 ? r + j - J0 : r + j;
                     }
+                };
+                uint32_t i = 0;
+                for (; i + 8 <= n; i += 8) {
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) w8[k] = ev[i + k];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) visit(i + k, w8[k]);
                 }
+                for (; i < n; i++) visit(i, ev[i]);
             }
             X.mcount[t] = cnt;
         } else if (he) {

@@ -14,7 +14,9 @@ pats = {
     "monkey": dict(keyword="monkey"), "abcde": dict(keyword="abcde"), "abwde": dict(keyword="ab*de", wildcard=ord("*")),
     "values10": dict(values=[10, 12, 15, 11, 30, 31, 29, 40, 41, 45]), "abclow16": dict(keyword="abc"), "abclow4": dict(keyword="abc"),
 }
-prog = m.Program(8, **pats[name])
+KANA = "あいうえおかきくけこさしすせそたちつてとなにぬねのはひふへほまみむめもやゆよらりるれろわをゃっゅょ"
+pats16 = {"kana6": dict(keyword="わたしたちは", char_seq=KANA), "mokeys": dict(keyword="mo*key*s", wildcard=ord("*"))}
+prog = m.Program(16, **pats16[name]) if name in pats16 else m.Program(8, **pats[name])
 for _ in range(3):
     r = prog.engine_scan(data, 524288)
     print(name, r.count, r.stats())
