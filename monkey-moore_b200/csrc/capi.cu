@@ -265,7 +265,7 @@ void enqueue_tiled(mmg_results *res) {
     // zero state
     const size_t o_status = carve(4 * sizeof(uint64_t));
     const size_t o_ticket = carve(2 * sizeof(uint32_t));
-    const size_t o_lookback = carve((size_t)G.nblocks * sizeof(uint64_t));
+    const size_t o_lookback = carve((size_t)G.nseg * sizeof(uint64_t));
     const size_t zero_need = off;
     off = 0;
     const size_t o_hasev = carve((size_t)G.nsub);
@@ -273,6 +273,9 @@ void enqueue_tiled(mmg_results *res) {
     const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
+    const size_t jp = (size_t)((P.Jmax + 15) / 16 * 16);
+    const size_t o_segmap = carve(G.segs_per_block > 1 ? (size_t)G.nseg * 2 * jp : 0);
+    const size_t o_segphase = carve(G.segs_per_block > 1 ? (size_t)G.nseg * 2 : 0);
     const size_t scratch_need = off;
     const bool zero_grew = zero_need > ws.zero_bytes;
     grow(ws.zero, ws.zero_bytes, zero_need, stream, true);
@@ -290,16 +293,18 @@ void enqueue_tiled(mmg_results *res) {
     X.sub_count = reinterpret_cast<uint32_t *>(ws.scratch + o_count);
     X.mcount = reinterpret_cast<uint32_t *>(ws.scratch + o_mcount);
     X.mbase = reinterpret_cast<uint64_t *>(ws.scratch + o_mbase);
+    X.segmap = ws.scratch + o_segmap;
+    X.segphase = ws.scratch + o_segphase;
     X.ev = ws.ev;
     X.ev_per_warp = (uint32_t)t.per_warp;
     X.host_status = res->status_host;             // pinned + mapped: same address on the device (UVA)
 
+    if (res->launches == 0) CU(cudaEventRecord(res->ev[1], stream));      // ev[1] -> ev[2] brackets the filter kernel alone
     CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
-    static const bool no_filter_event = getenv("MMG_NO_FILTER_EVENT") != nullptr;      // experiment
-    if (res->launches == 0 && !no_filter_event) CU(cudaEventRecord(res->ev[2], stream));
+    if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
     CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
     ws.dirty = false;
-    res->launches += 2;
+    res->launches += t.G.segs_per_block > 1 ? 4 : 2;
     t.generation = ++ws.generation;
 }
 
@@ -324,6 +329,16 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     if (spb > 0xFFFFFFFFull || nsub64 > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_ARG, "input too large for one scan")};
     G.spb = (uint32_t)spb;
     G.nsub = (uint32_t)nsub64;
+    // resolve geometry: segments of at most 128 sub-tiles
+    G.segs_per_block = (uint32_t)((spb + 127) / 128);
+    static const bool noseg = getenv("MMG_NOSEG") != nullptr;      // debug: one resolve CTA per engine block
+    if (noseg) G.segs_per_block = 1;
+    {
+        const uint64_t last_subs = nsub64 - (rq.nblocks - 1) * spb;            // sub-tiles of the last (possibly short) block
+        const uint64_t nseg64 = noseg ? rq.nblocks : (rq.nblocks - 1) * G.segs_per_block + (last_subs + 127) / 128;
+        if (nseg64 > 0x7FFFFFFFull) throw ScanError{fail(MMG_ERR_ARG, "input too large for one scan")};
+        G.nseg = (uint32_t)nseg64;
+    }
 
     int occ = 1;
     CU(mmg_filter_occupancy(W, t.lag_bytes, rq.big_endian, P.nkeys, &occ));
@@ -432,7 +447,7 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
             throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
         }
-        CU(cudaEventRecord(res->ev[1], stream));
+        if (mem == MMG_MEM_HOST) CU(cudaEventRecord(res->ev[1], stream));      // end of the copy (re-recorded before the filter)
         res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
         const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
         res->tiled = regular && g_path_override != 1;
@@ -440,6 +455,7 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         if (res->tiled) {
             launch_tiled(res, dev, lane.ws);
         } else {
+            CU(cudaEventRecord(res->ev[1], stream));
             run_generic(res->rq, stream, *res->arena, res, res->launches);
             CU(cudaEventRecord(res->ev[2], stream));
         }

@@ -551,7 +551,6 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
-    asm volatile("griddepcontrol.launch_dependents;");      // the resolve kernel's CTAs may take free SM resources now
 
     WarpState st;
     st.cursor = reg_lo;
@@ -727,7 +726,6 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     load_sprog(P);      // includes the only __syncthreads() of the kernel
-    asm volatile("griddepcontrol.launch_dependents;");      // the resolve kernel's CTAs may take free SM resources now
 
     // constants of the exact evaluation (volatile shared loads: see SProg)
     const volatile SProg &VP = g_sprog;
@@ -942,7 +940,7 @@ __device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom 
 #define RESOLVE_THREADS 128
 #define RESOLVE_FAST_J 16u
 
-template <int W, bool BE>
+template <int W, bool BE, bool MAPS_ONLY>
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
           uint64_t *out_off, uint32_t *out_val, uint64_t capacity, uint32_t jp) {
@@ -963,14 +961,17 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
-    if (tid == 0) { s_bi = atomicAdd(X.ticket, 1u); s_phase[0] = 0; s_phase[1] = 0; }
+    if (tid == 0) s_bi = MAPS_ONLY ? blockIdx.x : atomicAdd(X.ticket, 1u);
     __syncthreads();
     const uint32_t bi = s_bi;
-    // launched with programmatic stream serialization: everything above overlaps the tail of the filter kernel;
-    // its results (events, flags, status words) are visible only after this wait
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool bad = events_overflowed(X);
-    const uint32_t t_begin = bi * G.spb, t_end = min(t_begin + G.spb, G.nsub);
+    // segment bi = segment (bi mod segs_per_block) of engine block (bi / segs_per_block)
+    const uint32_t rb = bi / G.segs_per_block, si = bi - rb * G.segs_per_block;
+    const uint32_t t_begin = rb * G.spb + si * RESOLVE_THREADS;
+    const uint32_t t_end = G.segs_per_block == 1 ? min((rb + 1) * G.spb, G.nsub)
+                                                 : min(min(t_begin + RESOLVE_THREADS, (rb + 1) * G.spb), G.nsub);
+    if (tid < 2) s_phase[tid] = (MAPS_ONLY || si == 0) ? 0u : X.segphase[bi * 2 + tid];   // the chain restarts at every engine block
+    __syncthreads();
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
     const uint32_t magic = 65536u / J0 + 1u;      // q mod J0 = q - J0 * ((q * magic) >> 16), exact for q < 4096, J0 <= 16
     uint32_t total = 0;       // matches of this block (valid in every thread after the loop)
@@ -980,6 +981,11 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         const bool he = t < t_end && X.hasev[t] != 0;
         const uint32_t nvalid = min((uint32_t)RESOLVE_THREADS, t_end - tb);
         if (!__syncthreads_or(he)) {
+            if (MAPS_ONLY) {            // no events in the whole segment: every entry phase just follows its lattice
+                for (uint32_t i = tid; i < npads * Jmax; i += RESOLVE_THREADS)
+                    X.segmap[((size_t)bi * 2 + i / Jmax) * jp + i % Jmax] = (uint8_t)lattice_advance(i % Jmax, nvalid * NP, J0);
+                return;
+            }
             if (tid == 0)
                 for (uint32_t c = 0; c < npads; c++) s_phase[c] = lattice_advance(s_phase[c], nvalid * NP, J0);
             continue;
@@ -1042,6 +1048,30 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             }
         }
         __syncthreads();
+        if (MAPS_ONLY) {
+            // (b') the map of the whole segment: lane e follows entry phase e through the sub-tile maps (a segment is
+            // one round, so this is all the kernel has to produce)
+            if (wid < (int)npads) {
+                const uint32_t c = wid;
+                for (uint32_t e0 = 0; e0 < Jmax; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    uint32_t ph = e < Jmax ? e : 0u, done = 0;
+                    for (uint32_t g = 0; g < RESOLVE_THREADS && g < nvalid; g += 32) {
+                        uint32_t m = __ballot_sync(FULL, g + lane < nvalid && s_has[(g + lane) * 2 + c]);
+                        while (m) {
+                            const uint32_t l = g + __ffs(m) - 1;
+                            m &= m - 1;
+                            if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);
+                            ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * RESOLVE_THREADS + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
+                            done = l + 1;
+                        }
+                    }
+                    if (nvalid > done) ph = lattice_advance(ph, (nvalid - done) * NP, J0);
+                    if (e < Jmax) X.segmap[((size_t)bi * 2 + c) * jp + e] = (uint8_t)ph;
+                }
+            }
+            return;
+        }
         // (b) phases: warp c composes the maps of class c over the sub-tiles of this round, in order
         if (wid < (int)npads) {
             const uint32_t c = wid;
@@ -1115,6 +1145,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         __syncthreads();
     }
 
+    if (MAPS_ONLY) return;       // (an overflowed event buffer skips the loop: nothing to do, the resolve kernel reports it)
+
     // (d) base of this block in the output: decoupled look-back, 8 x 32 predecessors per step (the eight
     // window loads are independent, so a block far from the nearest inclusive prefix still needs few round trips)
     if (wid == 0) {
@@ -1150,7 +1182,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         if (lane == 0) {
             lb[bi] = LB_INCL | (before + total);
             s_before = before;
-            if (bi == G.nblocks - 1) X.status[2] = before + total;
+            if (bi == G.nseg - 1) X.status[2] = before + total;
         }
     }
     __syncthreads();
@@ -1196,7 +1228,41 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         __syncthreads();
         if (tid < 4) X.status[tid] = 0;
         if (tid < 2) X.ticket[tid] = 0;
-        for (uint32_t i = tid; i < G.nblocks; i += RESOLVE_THREADS) X.lookback[i] = 0;
+        for (uint32_t i = tid; i < G.nseg; i += RESOLVE_THREADS) X.lookback[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: entry phase of every segment of a block that is cut into several segments: the chain enters segment 0 with
+// phase 0 and segment k+1 with segmap[k][phase of k].  One warp per engine block; the maps of 32 segments at a
+// time are staged in shared memory with coalesced loads, the dependent look-ups then run at shared-memory latency.
+// ------------------------------------------------------------------------------------------
+
+#define SEGPHASE_WARPS 4
+
+__global__ void __launch_bounds__(SEGPHASE_WARPS * 32)
+k_segphase(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X, uint32_t jp) {
+    extern __shared__ __align__(16) uint8_t sp_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t rb = blockIdx.x * SEGPHASE_WARPS + wid;
+    if (rb >= G.nblocks) return;
+    const uint32_t row = 2u * jp;                           // bytes of one segment's maps (both classes)
+    uint8_t *stage = sp_smem + (size_t)wid * 32u * row;
+    const uint32_t first = rb * G.segs_per_block;
+    const uint32_t nseg = min(G.segs_per_block, G.nseg - first);
+    uint32_t ph = 0;                                        // lanes 0 and 1 follow classes 0 and 1
+    for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
+        const uint32_t ns = min(32u, nseg - s0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(X.segmap + (size_t)(first + s0) * row);
+        for (uint32_t i = lane; i < ns * row / 16u; i += 32) reinterpret_cast<uint4 *>(stage)[i] = src[i];
+        __syncwarp();
+        if (lane < (int)G.npads) {
+            for (uint32_t k = 0; k < ns; k++) {
+                X.segphase[(size_t)(first + s0 + k) * 2 + lane] = (uint8_t)ph;
+                ph = stage[k * row + lane * jp + ph];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1444,22 +1510,24 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
 
 cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
                                uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
-    const unsigned grid = G.nblocks;                 // one CTA per engine block
+    const unsigned grid = G.nseg;                    // one CTA per segment (= engine block while blocks have <= 128 sub-tiles)
     const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
     const bool fast = P.J0 == P.Jmax && (uint32_t)P.Jmax <= RESOLVE_FAST_J;
     const size_t smem = (fast ? (size_t)RESOLVE_THREADS * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
                         RESOLVE_THREADS * 4;
-    // programmatic dependent launch: the CTAs become resident while the filter kernel is still running and wait at
-    // griddepcontrol.wait, so launch latency and block scheduling are off the critical path
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(RESOLVE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (P.W == 1) return cudaLaunchKernelEx(&cfg, k_resolve<1, false>, P, G, X, out_off, out_val, capacity, jp);
-    if (G.big_endian) return cudaLaunchKernelEx(&cfg, k_resolve<2, true>, P, G, X, out_off, out_val, capacity, jp);
-    return cudaLaunchKernelEx(&cfg, k_resolve<2, false>, P, G, X, out_off, out_val, capacity, jp);
+    if (G.segs_per_block > 1) {
+        // blocks cut into segments: segment maps, then the phase prefix along each block
+        if (P.W == 1) k_resolve<1, false, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+        else if (G.big_endian) k_resolve<2, true, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+        else k_resolve<2, false, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+        k_segphase<<<(G.nblocks + SEGPHASE_WARPS - 1) / SEGPHASE_WARPS, SEGPHASE_WARPS * 32, (size_t)SEGPHASE_WARPS * 32 * 2 * jp, stream>>>(G, X, jp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (P.W == 1) k_resolve<1, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else if (G.big_endian) k_resolve<2, true, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else k_resolve<2, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    return cudaGetLastError();
 }
 
 // exclusive scan of n u32 counts into u64 bases; bsum must hold ceil(n/1024) entries; *total receives the sum

@@ -49,6 +49,11 @@ struct MmgGeom {
     uint32_t nsub;         // total sub-tiles (fast path)
     uint32_t chunk_subs;   // sub-tiles per warp work unit (divides spb)
     uint32_t nchunks;
+    // resolve geometry: one CTA per SEGMENT of at most 128 sub-tiles; a block of more than 128 sub-tiles (search() on a
+    // large buffer, the GUI's 8 MiB blocks) is cut into segs_per_block segments whose entry phases come from a prefix
+    // over the segment maps (k_segmaps, k_segphase)
+    uint32_t segs_per_block;
+    uint32_t nseg;         // total segments = CTAs of the resolve kernel
 };
 
 struct MmgScratch {
@@ -66,6 +71,8 @@ struct MmgScratch {
     uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts
     uint32_t *ticket;      // [0] block ticket of the resolve kernel  [1] CTAs of the resolve kernel that are done
     uint64_t *host_status; // pinned, device-visible: receives status[0..3] when the resolve kernel ends
+    uint8_t *segmap;       // [nseg][2][jp] entry phase -> exit phase of a whole segment (only when segs_per_block > 1)
+    uint8_t *segphase;     // [nseg][2] entry phase of the segment
 };
 
 #endif

@@ -157,3 +157,25 @@ def test_sharded_scan_equals_whole(gpu):
             parts.append(prog.engine_scan(np.ascontiguousarray(fb[lo:hi]), block, file_size=len(fb),
                                           first_block=b0, num_blocks=b1 - b0).offsets)
         assert np.concatenate(parts).tolist() == whole.tolist()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_engine_big_blocks(gpu, seed):
+    """Engine blocks of more than 128 sub-tiles (the GUI's 8 MiB default, src/gui/monkey_prefs.cpp:26) are resolved in
+    segments: segment maps, phase prefix along the block, then the usual replay -- same results as one chain per block."""
+    rng = np.random.default_rng(4000 + seed)
+    hits = 0
+    for _ in range(6):
+        bits = int(rng.choice([8, 16]))
+        pat = random_pattern(rng, bits)
+        try:
+            Oracle(bits, **pat_kwargs(pat))
+        except OracleError:
+            continue
+        n = int(rng.choice([1500000, 2500001, 5000000]))
+        data = random_data(rng, bits, n, pat)
+        fb = np.ascontiguousarray(data).view(np.uint8)
+        block = int(rng.choice([1 << 20, 2 << 20, 8 << 20, 528384]))
+        be = bool(rng.random() < 0.4)
+        hits += check_engine(gpu, bits, pat, fb, block, be)
+    assert hits > 0
