@@ -2,9 +2,12 @@
 //
 // Replaces the reference's src/core/search_engine.cpp.  What is gone: one ifstream + one
 // std::async thread per block, a full buffer copy per alignment, the in-place byte swap and the
-// dispatcher's 5 ms polling sleep (:104-188).  What replaces it: the file is read in large slabs
-// of whole blocks into page-locked memory and each slab is handed to mmg_engine_scan, which runs
-// every (block, alignment) chain on the GPU in one pass and returns offsets already sorted.
+// dispatcher's 5 ms polling sleep (:104-188).  What replaces it: the file is read in slabs of whole
+// blocks into two page-locked buffers (several threads pread() disjoint pieces of a slab) and each
+// slab is handed to mmg_engine_scan_async, which copies it to the GPU and runs every (block,
+// alignment) chain there in one pass; while slab k is copied and scanned the host already reads
+// slab k+1, and the library's two internal streams let the copy of k+1 overlap the scan of k.
+// Offsets come back already sorted.
 // What is kept exactly: block geometry (:218-253), the callback protocol and abort contract
 // (:47, :80, :161-165, :177-187, :191), "File not found" (:43-45), result order (:193-197) and the
 // preview text (:256-348, including the sticky stream state of the shared ifstream).
@@ -12,13 +15,19 @@
 
 #include "mmoore_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <iomanip>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 namespace {
 
@@ -52,8 +61,9 @@ std::string to_utf8(char32_t cp) {
 
 struct PinnedBuffer {
    uint8_t *ptr = nullptr;
+   uint64_t size = 0;
    bool pinned = false;
-   explicit PinnedBuffer(uint64_t n) {
+   explicit PinnedBuffer(uint64_t n) : size(n) {
       ptr = static_cast<uint8_t *>(mmg_host_alloc(n));
       pinned = ptr != nullptr;
       if (!ptr) ptr = static_cast<uint8_t *>(::operator new(n ? n : 1));
@@ -64,7 +74,68 @@ struct PinnedBuffer {
    }
 };
 
-constexpr uint64_t kSlabBytes = 256ull << 20;   // bytes of whole blocks handed to one GPU scan
+// Page-locking memory costs milliseconds per slab, a GUI session runs search after search: the staging slabs are
+// kept in a small process-wide pool instead of being pinned and released by every run().
+class StagingPool {
+ public:
+   std::unique_ptr<PinnedBuffer> take(uint64_t n) {
+      {
+         std::lock_guard<std::mutex> lock(mutex_);
+         for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i]->size >= n) {
+               auto b = std::move(free_[i]);
+               free_.erase(free_.begin() + static_cast<std::ptrdiff_t>(i));
+               return b;
+            }
+      }
+      return std::make_unique<PinnedBuffer>(n);
+   }
+   void give(std::unique_ptr<PinnedBuffer> b) {
+      if (!b) return;
+      std::lock_guard<std::mutex> lock(mutex_);
+      if (free_.size() < 4) free_.push_back(std::move(b));      // at most 4 slabs stay pinned
+   }
+ private:
+   std::mutex mutex_;
+   std::vector<std::unique_ptr<PinnedBuffer>> free_;
+};
+
+StagingPool &staging_pool() {
+   static StagingPool *pool = new StagingPool();      // never destroyed: no CUDA calls during static destruction
+   return *pool;
+}
+
+constexpr uint64_t kSlabBytes = 32ull << 20;    // bytes of whole blocks handed to one GPU scan
+constexpr uint64_t kReadPiece = 2ull << 20;     // smallest piece one reader thread takes
+
+// Reads file bytes [lo, lo + len) into dst with several threads (pread on one descriptor); bytes the file no longer
+// has (it shrank underneath us) are zero.
+void read_range(int fd, uint64_t lo, uint64_t len, uint8_t *dst) {
+   auto piece = [fd](uint64_t at, uint64_t n, uint8_t *out) {
+      uint64_t done = 0;
+      while (done < n) {
+         const ssize_t got = ::pread(fd, out + done, n - done, static_cast<off_t>(at + done));
+         if (got <= 0) break;
+         done += static_cast<uint64_t>(got);
+      }
+      if (done < n) std::memset(out + done, 0, n - done);
+   };
+   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+   const uint64_t want = std::min<uint64_t>(std::min<uint64_t>(hw, 16), (len + kReadPiece - 1) / kReadPiece);
+   if (want <= 1) { piece(lo, len, dst); return; }
+   const uint64_t step = ((len + want - 1) / want + 4095) & ~4095ull;
+   std::vector<std::thread> readers;
+   for (uint64_t at = step; at < len; at += step)
+      readers.emplace_back(piece, lo + at, std::min(step, len - at), dst + at);
+   piece(lo, std::min(step, len), dst);
+   for (auto &t : readers) t.join();
+}
+
+struct FileDescriptor {
+   int fd;
+   explicit FileDescriptor(const std::filesystem::path &p) : fd(::open(p.c_str(), O_RDONLY)) {}
+   ~FileDescriptor() { if (fd >= 0) ::close(fd); }
+};
 
 }  // namespace
 
@@ -95,28 +166,36 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
    on_progress(0, mmoore::SearchStep::Searching);
 
    if (num_blocks > 0) {
-      std::ifstream file(config.file_path, std::ios::binary);
-      if (!file.is_open()) throw std::runtime_error("Worker thread failed to open file: " + config.file_path.string());
+      FileDescriptor file(config.file_path);
+      if (file.fd < 0) throw std::runtime_error("Worker thread failed to open file: " + config.file_path.string());
 
       const uint64_t blocks_per_slab = std::max<uint64_t>(1, kSlabBytes / block);
       const uint64_t slab_capacity = std::min<uint64_t>(file_size, blocks_per_slab * block + overlap);
-      PinnedBuffer slab(slab_capacity);
       const bool big_endian = config.endianness == mmoore::Endianness::Big;
 
-      for (uint64_t first = 0; first < num_blocks; first += blocks_per_slab) {
-         const uint64_t n = std::min<uint64_t>(blocks_per_slab, num_blocks - first);
-         const uint64_t lo = first * block;
-         const uint64_t hi = std::min<uint64_t>(file_size, (first + n) * static_cast<uint64_t>(block) + overlap);
-         file.clear();
-         file.seekg(static_cast<std::streamoff>(lo));
-         file.read(reinterpret_cast<char *>(slab.ptr), static_cast<std::streamsize>(hi - lo));
-         const uint64_t got = static_cast<uint64_t>(file.gcount());
-         if (got < hi - lo) std::memset(slab.ptr + got, 0, hi - lo - got);   // file shrank underneath us
-
+      // two slabs in flight: [read k+1 on the host]  ||  [H2D + scan of k on the GPU]
+      struct Slot {
+         std::unique_ptr<PinnedBuffer> buf;
          mmg_results *res = nullptr;
-         const int rc = mmg_engine_scan(searcher->program(), slab.ptr, hi - lo, MMG_MEM_HOST, file_size, block, first, n,
-                                        big_endian ? 1 : 0, &res);
-         if (rc != MMG_OK) throw_last(rc);
+         uint64_t blocks = 0;
+      } slots[2];
+      struct Pending {     // pending scans are completed (or dropped) before the buffers they read go back to the pool
+         Slot *s;
+         ~Pending() {
+            for (int i = 0; i < 2; i++) {
+               if (s[i].res) mmg_results_free(s[i].res);
+               staging_pool().give(std::move(s[i].buf));
+            }
+         }
+      } pending{slots};
+
+      // completes the scan of a slot: results in file order, then one callback per block of the slab, exactly as the
+      // reference's workers report (float accumulation included); false = aborted
+      auto collect = [&](Slot &slot) -> bool {
+         mmg_results *res = slot.res;
+         slot.res = nullptr;
+         const int rc = mmg_results_wait(res);
+         if (rc != MMG_OK) { mmg_results_free(res); throw_last(rc); }
          const uint64_t count = mmg_results_count(res);
          if (count) {
             std::vector<uint64_t> offsets(count);
@@ -128,14 +207,32 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
                results.push_back({offsets[i], searcher->table_from_values(values[2 * i], values[2 * i + 1]), std::string()});
          }
          mmg_results_free(res);
-
-         // one callback per block, exactly as the reference's workers report (float accumulation included)
-         for (uint64_t b = 0; b < n; b++) {
+         for (uint64_t b = 0; b < slot.blocks; b++) {
             total_progress += progress_increment;
             on_progress(static_cast<int>(total_progress), SearchStep::Searching);
-            if (abort_flag) return {};
+            if (abort_flag) return false;
          }
+         return true;
+      };
+
+      uint64_t k = 0;
+      for (uint64_t first = 0; first < num_blocks; first += blocks_per_slab, k++) {
+         Slot &slot = slots[k & 1];
+         if (slot.res && !collect(slot)) return {};          // slab k-2 used this buffer
+         if (abort_flag) return {};
+         if (!slot.buf) slot.buf = staging_pool().take(slab_capacity);
+         const uint64_t n = std::min<uint64_t>(blocks_per_slab, num_blocks - first);
+         const uint64_t lo = first * block;
+         const uint64_t hi = std::min<uint64_t>(file_size, (first + n) * static_cast<uint64_t>(block) + overlap);
+         read_range(file.fd, lo, hi - lo, slot.buf->ptr);
+         const int rc = mmg_engine_scan_async(searcher->program(), slot.buf->ptr, hi - lo, MMG_MEM_HOST, file_size, block,
+                                              first, n, big_endian ? 1 : 0, &slot.res);
+         if (rc != MMG_OK) throw_last(rc);
+         slot.blocks = n;
       }
+      // the last two slabs, oldest first
+      for (uint64_t j = k >= 2 ? k - 2 : 0; j < k; j++)
+         if (slots[j & 1].res && !collect(slots[j & 1])) return {};
    }
    if (abort_flag) return {};
 
