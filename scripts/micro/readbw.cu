@@ -1,0 +1,134 @@
+// Development microbenchmark: achievable read bandwidth of different streaming access patterns on one B200.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o readbw readbw.cu && ./readbw [MiB]
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1);} } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do { asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory"); } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr)); return r; }
+
+// (1) classic grid-stride 16-byte loads, UNR loads in flight per thread
+template <int UNR>
+__global__ void __launch_bounds__(256) k_ldg(const uint4 *p, uint64_t n, uint32_t *out) {
+    uint32_t acc = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNR - 1) * stride < n; i += UNR * stride) {
+        uint4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) v[u] = __ldcs(p + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNR; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    for (; i < n; i += stride) { uint4 v = p[i]; acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+// (2) per-warp private chunks, per-warp TMA ring of NST stages of STAGE bytes; chunk = CH bytes drawn from a counter
+// MODE 0: warp-private chunks.  MODE 1: CTA-cooperative: the CTA draws a chunk of 8*CH bytes, warp w takes stages w, w+8, ...
+template <int STAGE, int NST, int MODE, int HALO>
+__global__ void __launch_bounds__(256) k_tma(const uint8_t *p, uint64_t n, uint32_t CH, unsigned long long *ctr, uint32_t *out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t *ring = smem + (size_t)wib * (NST * (STAGE + HALO) + 64);
+    const uint32_t ring_a = smem_u32(ring), bar_a = ring_a + NST * (STAGE + HALO);
+    __shared__ uint32_t s_chunk;
+    if (lane == 0) { for (int i = 0; i < NST; i++) mbar_init(bar_a + 8 * i, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    uint32_t acc = 0, slot = 0, parity = 0;
+    const uint64_t nchunks = n / CH;
+    uint32_t iter = 0;
+    for (;;) {
+        uint64_t base; uint32_t nst, step;
+        if (MODE == 2) {
+            const uint32_t c = (blockIdx.x * 8 + wib) + iter * gridDim.x * 8;
+            iter++;
+            if (c >= nchunks) break;
+            base = (uint64_t)c * CH; nst = CH / STAGE; step = STAGE;
+        } else if (MODE == 0) {
+            uint32_t c = 0;
+            if (lane == 0) c = (uint32_t)atomicAdd(ctr, 1ull);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= nchunks) break;
+            base = (uint64_t)c * CH; nst = CH / STAGE; step = STAGE;
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_chunk = (uint32_t)atomicAdd(ctr, 1ull);
+            __syncthreads();
+            const uint32_t c = s_chunk;
+            if ((uint64_t)c * 8 + 8 > nchunks) break;
+            base = (uint64_t)c * CH * 8 + (uint64_t)wib * STAGE; nst = CH / STAGE; step = STAGE * 8;
+        }
+        if (lane == 0)
+            for (uint32_t k = 0, sl = slot; k < nst && k < NST; k++) {
+                mbar_expect_tx(bar_a + 8 * sl, STAGE + HALO);
+                tma_load_1d(ring_a + sl * (STAGE + HALO), p + base + (uint64_t)k * step - HALO, STAGE + HALO, bar_a + 8 * sl);
+                sl = sl + 1 == NST ? 0 : sl + 1;
+            }
+        for (uint32_t k = 0; k < nst; k++) {
+            mbar_wait(bar_a + 8 * slot, parity);
+            for (uint32_t r = 0; r < STAGE / 512; r++) { uint4 v = lds128(ring_a + slot * (STAGE + HALO) + r * 512 + lane * 16); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+            __syncwarp();
+            if (lane == 0 && k + NST < nst) {
+                mbar_expect_tx(bar_a + 8 * slot, STAGE + HALO);
+                tma_load_1d(ring_a + slot * (STAGE + HALO), p + base + (uint64_t)(k + NST) * step - HALO, STAGE + HALO, bar_a + 8 * slot);
+            }
+            if (++slot == NST) { slot = 0; parity ^= 1u; }
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <class F> float timeit(F f, int iters = 10) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); f();
+    float best = 1e9;
+    for (int i = 0; i < iters; i++) { cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms; }
+    return best;
+}
+
+template <int STAGE, int NST, int MODE, int HALO = 0> void run_tma(const uint8_t *d, uint64_t n, uint32_t CH, int ctas_per_sm, unsigned long long *ctr, uint32_t *out) {
+    const size_t smem = 8 * (NST * (STAGE + HALO) + 64);
+    CK(cudaFuncSetAttribute(k_tma<STAGE, NST, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tma<STAGE, NST, MODE, HALO>, 256, smem);
+    if (occ > ctas_per_sm) occ = ctas_per_sm;
+    float ms = timeit([&] { cudaMemsetAsync(ctr, 0, 8); k_tma<STAGE, NST, MODE, HALO><<<148 * occ, 256, smem>>>(d, n, CH, ctr, out); });
+    printf("tma mode=%d stage=%5d halo=%d nst=%d chunk=%7u ctas/sm=%d : %.3f ms  %.0f GB/s\n", MODE, STAGE, HALO, NST, CH, occ, ms, n / ms / 1e6);
+}
+
+int main(int argc, char **argv) {
+    const uint64_t n = (uint64_t)(argc > 1 ? atoi(argv[1]) : 512) << 20;
+    uint8_t *d; uint32_t *out; unsigned long long *ctr;
+    CK(cudaMalloc(&d, n)); CK(cudaMalloc(&out, 4)); CK(cudaMalloc(&ctr, 8));
+    CK(cudaMemset(d, 1, n));
+    for (int g : {148 * 4, 148 * 8, 148 * 16, 148 * 32}) {
+        float ms = timeit([&] { k_ldg<4><<<g, 256>>>((const uint4 *)d, n / 16, out); });
+        printf("ldg unroll 4 grid=%5d : %.3f ms  %.0f GB/s\n", g, ms, n / ms / 1e6);
+        ms = timeit([&] { k_ldg<8><<<g, 256>>>((const uint4 *)d, n / 16, out); });
+        printf("ldg unroll 8 grid=%5d : %.3f ms  %.0f GB/s\n", g, ms, n / ms / 1e6);
+    }
+    {   // empty kernel: launch + event overhead
+        float ms = timeit([&] { k_ldg<4><<<1, 32>>>((const uint4 *)d, 0, out); });
+        printf("empty launch: %.4f ms\n", ms);
+    }
+    for (uint32_t ch : {4096u, 8192u, 16384u, 32768u, 65536u}) {
+        run_tma<4096, 2, 0, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+        run_tma<4096, 2, 2, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+        run_tma<2048, 3, 0, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+        run_tma<2048, 3, 2, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+        run_tma<4096, 2, 1, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}

@@ -21,10 +21,13 @@ cases = [
     ("8 values10", 8, dict(values=[10, 12, 15, 11, 30, 31, 29, 40, 41, 45]), data, False),
     ("8 abc low16", 8, dict(keyword="abc"), low, False),
 ]
+sel = os.environ.get("PROBE_CASES")
+if sel:
+    cases = [c for c in cases if any(c[0].startswith(t) for t in sel.split(","))]
 for name, bits, pat, buf, be in cases:
     prog = m.Program(bits, **pat)
     best = None
-    for it in range(4):
+    for it in range(int(os.environ.get('PROBE_ITERS', '4'))):
         r = prog.engine_scan(buf, 524288, big_endian=be)
         st = r.stats(); n = r.count; r.close()
         if best is None or st["ms_total"] < best["ms_total"]:
