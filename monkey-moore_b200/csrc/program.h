@@ -37,6 +37,10 @@ struct MmgProgram {
     int32_t first_lit;    // keyword index whose element yields the table base value (v0)
     int32_t opp_idx;      // keyword index of the first opposite-case letter (v1), or -1
     int32_t nkeys;        // filter keys; -1 => every window must be evaluated exactly
+    // 16-bit pre-filter, range stage (multi-key patterns whose keys cluster, e.g. differences of character-sequence
+    // indices): every key k satisfies (k - rng_lo) mod 2^16 <= rng_w.  rng_c = the SWAR constant (upper half 1 - rng_lo,
+    // lower half -rng_lo); rng_w = 0xFFFFFFFF disables the stage.
+    uint32_t rng_c, rng_w;
     int32_t d2ok;         // 8-bit filter may refine "comparison 0 passes" candidates with comparison 1 (see filter_lane)
     // Differences (mod 2^(8W)) of comparison 0 that do NOT lead to a J0 advance, stored as the
     // SWAR constant the filter kernel consumes:  W=1: k * 0x01010101 ;  W=2: ((1-k) & 0xFFFF) * 0x00010001

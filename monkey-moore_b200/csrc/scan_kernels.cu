@@ -252,6 +252,18 @@ __device__ __forceinline__ bool prefilter16(const MmgProgram &P, const uint32_t 
         uint32_t d[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) d[k] = cur[k] - prv[k];
+        if (P.rng_w != 0xFFFFFFFFu) {
+            // range stage: does any difference of the row fall into the arc that holds all keys?  (upper halves carry
+            // the borrow slack of the 32-bit subtraction: + 1)
+            const uint32_t c = P.rng_c;
+            uint32_t a0 = __viaddmin_u16x2(d[0], c, 0xFFFFFFFFu), a1 = __viaddmin_u16x2(d[1], c, 0xFFFFFFFFu);
+            a0 = __viaddmin_u16x2(d[2], c, a0); a1 = __viaddmin_u16x2(d[3], c, a1);
+            a0 = __viaddmin_u16x2(d[4], c, a0); a1 = __viaddmin_u16x2(d[5], c, a1);
+            a0 = __viaddmin_u16x2(d[6], c, a0); a1 = __viaddmin_u16x2(d[7], c, a1);
+            const uint32_t a = __vminu2(a0, a1);
+            const bool maybe = ((a & 0xFFFFu) <= P.rng_w) || ((a >> 16) <= P.rng_w + 1u);
+            if (!__any_sync(FULL, maybe)) return false;
+        }
         const int nk = P.nkeys;
         uint32_t a4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};      // four independent min chains
 #pragma unroll 2
