@@ -118,6 +118,12 @@ int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t 
  * as u32[count] = v0 | v1 << 16.  For NCCL gathers without a host round trip. */
 const uint64_t *mmg_results_device_offsets(const mmg_results *r);
 const uint32_t *mmg_results_device_values(const mmg_results *r);
+/* Distinct inferred tables of a match list -- the GUI's default "one row per table" view
+ * (src/gui/monkey_frame.cpp:1236-1245: a result is listed iff no earlier result has an equal values map).
+ * Writes to `indices` (room for `capacity` entries; may be NULL) the ascending match-list indices of the FIRST match
+ * of every distinct table and stores their number in *n_unique (call with capacity 0 to size the buffer).  The
+ * reduction runs on the device over the values the scan emitted; the match list does not travel to the host. */
+int mmg_results_unique(const mmg_program *p, const mmg_results *r, uint64_t *indices, uint64_t capacity, uint64_t *n_unique);
 void mmg_results_free(mmg_results *r);
 
 /* Timing / accounting of the last scan that produced `r` (for bench.py). */

@@ -32,7 +32,7 @@ C_ABI_SYMBOLS = [
     "mmg_last_error", "mmg_device_count", "mmg_program_create_keyword", "mmg_program_create_values",
     "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_engine_scan_async", "mmg_results_wait", "mmg_num_blocks", "mmg_results_count",
-    "mmg_results_copy", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
+    "mmg_results_copy", "mmg_results_unique", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
     "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
     "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_gathered_count",
     "mmg_gathered_copy", "mmg_gathered_free",
@@ -94,6 +94,7 @@ def lib():
         l.mmg_results_count.restype = C.c_uint64
         l.mmg_results_count.argtypes = [C.c_void_p]
         l.mmg_results_copy.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _u64p, _u32p]
+        l.mmg_results_unique.argtypes = [C.c_void_p, C.c_void_p, _u64p, C.c_uint64, _u64p]
         l.mmg_results_device_offsets.restype = C.c_void_p
         l.mmg_results_device_offsets.argtypes = [C.c_void_p]
         l.mmg_results_device_values.restype = C.c_void_p
@@ -191,6 +192,16 @@ class Results:
     @property
     def offsets(self):
         return self.arrays()[0]
+
+    def unique_indices(self):
+        """Indices (ascending) of the first match of every distinct inferred table -- the reference GUI's default
+        "one row per table" view (src/gui/monkey_frame.cpp:1236-1245), reduced on the device."""
+        n = C.c_uint64(0)
+        _check(lib().mmg_results_unique(self._program._h, self._h, None, 0, C.byref(n)))
+        idx = np.zeros(n.value, np.uint64)
+        if n.value:
+            _check(lib().mmg_results_unique(self._program._h, self._h, idx.ctypes.data_as(_u64p), n.value, C.byref(n)))
+        return idx
 
     def device_pointers(self):
         return lib().mmg_results_device_offsets(self._h), lib().mmg_results_device_values(self._h)

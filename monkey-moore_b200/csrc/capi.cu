@@ -636,6 +636,75 @@ int mmg_results_copy(const mmg_results *r, uint64_t first, uint64_t n, uint64_t 
     return MMG_OK;
 }
 
+// Distinct inferred tables: see unique.cu.
+int mmg_results_unique(const mmg_program *p, const mmg_results *r, uint64_t *indices, uint64_t capacity, uint64_t *n_unique) {
+    if (!p || !r || !n_unique) return fail(MMG_ERR_ARG, "null argument");
+    done(r);
+    if (r->error != MMG_OK) return r->error;
+    *n_unique = 0;
+    const uint64_t M = r->count;
+    if (M == 0) return MMG_OK;
+    // which of the two emitted element values the table depends on (mirrors mmg_program_table)
+    uint32_t keymask = 0xFFFFu;
+    if (p->mode == 2) keymask = 0;                                                   // value scan: no table at all
+    else if (p->char_seq.empty() && p->mode == 1 && p->has_case_change && p->dev.opp_idx >= 0) keymask = 0xFFFFFFFFu;
+    std::vector<uint64_t> firsts;
+    if (keymask == 0) {
+        firsts.push_back(0);
+    } else {
+        cudaStream_t stream = r->stream;
+        try {
+            if (keymask == 0xFFFFu || p->elem_bits == 8) {
+                uint64_t *d_first = nullptr;
+                CU(cudaMallocAsync((void **)&d_first, 65536 * sizeof(uint64_t), stream));
+                CU(cudaMemsetAsync(d_first, 0xFF, 65536 * sizeof(uint64_t), stream));
+                CU(mmg_launch_unique_direct(r->d_val, M, keymask, keymask != 0xFFFFu, d_first, stream));
+                std::vector<uint64_t> table(65536);
+                CU(cudaMemcpyAsync(table.data(), d_first, 65536 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+                CU(cudaFreeAsync(d_first, stream));
+                CU(cudaStreamSynchronize(stream));
+                for (uint64_t v : table)
+                    if (v != ~0ull) firsts.push_back(v);
+            } else {
+                if (M >= 0xFFFFFFFFull) return fail(MMG_ERR_NOMEM, "match list too long for the hashed unique-table pass");
+                uint64_t cap = 1024;
+                while (cap < 2 * M && cap < (1ull << 28)) cap <<= 1;
+                uint64_t *d_slots = nullptr, *d_out = nullptr, *d_cnt = nullptr;
+                const uint64_t out_cap = std::min<uint64_t>(M, cap);
+                CU(cudaMallocAsync((void **)&d_slots, cap * sizeof(uint64_t), stream));
+                CU(cudaMallocAsync((void **)&d_out, out_cap * sizeof(uint64_t), stream));
+                CU(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(uint64_t), stream));
+                CU(cudaMemsetAsync(d_slots, 0xFF, cap * sizeof(uint64_t), stream));
+                CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(uint64_t), stream));
+                CU(mmg_launch_unique_hash(r->d_val, M, d_slots, (uint32_t)(cap - 1), reinterpret_cast<unsigned int *>(d_cnt + 1), stream));
+                CU(mmg_launch_unique_collect(d_slots, cap, true, d_out, d_cnt, out_cap, stream));
+                uint64_t h_cnt[2] = {0, 0};
+                CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream));
+                const bool overflow = (h_cnt[1] & 0xFFFFFFFFull) != 0;
+                if (!overflow) {
+                    firsts.resize(std::min<uint64_t>(h_cnt[0], out_cap));
+                    if (!firsts.empty())
+                        CU(cudaMemcpyAsync(firsts.data(), d_out, firsts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+                }
+                CU(cudaFreeAsync(d_slots, stream));
+                CU(cudaFreeAsync(d_out, stream));
+                CU(cudaFreeAsync(d_cnt, stream));
+                CU(cudaStreamSynchronize(stream));
+                if (overflow) return fail(MMG_ERR_NOMEM, "more distinct tables than the hashed unique-table pass can hold");
+            }
+        } catch (const ScanError &e) {
+            cudaGetLastError();
+            return e.code;
+        }
+        std::sort(firsts.begin(), firsts.end());
+    }
+    *n_unique = firsts.size();
+    if (indices)
+        for (uint64_t i = 0; i < firsts.size() && i < capacity; i++) indices[i] = firsts[i];
+    return MMG_OK;
+}
+
 const uint64_t *mmg_results_device_offsets(const mmg_results *r) { return r ? done(r)->d_off : nullptr; }
 const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? done(r)->d_val : nullptr; }
 

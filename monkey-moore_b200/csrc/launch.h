@@ -20,6 +20,14 @@ cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, c
                                      const uint64_t *in_off, const uint32_t *in_val, uint64_t *out_off,
                                      uint32_t *out_val, cudaStream_t stream);
 
+// distinct tables of a match list (unique.cu)
+cudaError_t mmg_launch_unique_direct(const uint32_t *val, uint64_t n, uint32_t keymask, bool pack8, uint64_t *first,
+                                     cudaStream_t stream);
+cudaError_t mmg_launch_unique_hash(const uint32_t *val, uint64_t n, uint64_t *slots, uint32_t capmask, unsigned int *overflow,
+                                   cudaStream_t stream);
+cudaError_t mmg_launch_unique_collect(const uint64_t *slots, uint64_t nslots, bool low32, uint64_t *out, uint64_t *count,
+                                      uint64_t capacity, cudaStream_t stream);
+
 cudaError_t mmg_launch_synth(uint64_t *out, uint64_t nwords, uint64_t seed, uint64_t first_word, uint32_t byte_mask,
                              cudaStream_t stream);
 

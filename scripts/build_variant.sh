@@ -8,10 +8,10 @@ NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
 OBJ=../../gpurun_variants/obj
 mkdir -p $OBJ
-for f in capi.cu comm.cu pattern.cpp; do
+for f in capi.cu comm.cu unique.cu pattern.cpp; do
   o=$OBJ/${f%.*}.o
   if [ ! -f $o ] || [ $f -nt $o ] || [ scan_kernels.cuh -nt $o ] || [ program.h -nt $o ]; then $NVCC $FLAGS -c -o $o $f; fi
 done
 $NVCC $FLAGS $@ -c -o $OBJ/scan_kernels_$NAME.o scan_kernels.cu
-$NVCC $FLAGS -shared -o ../../gpurun_variants/lib_$NAME.so $OBJ/capi.o $OBJ/comm.o $OBJ/pattern.o $OBJ/scan_kernels_$NAME.o -lcudart -ldl
+$NVCC $FLAGS -shared -o ../../gpurun_variants/lib_$NAME.so $OBJ/capi.o $OBJ/comm.o $OBJ/unique.o $OBJ/pattern.o $OBJ/scan_kernels_$NAME.o -lcudart -ldl
 echo built lib_$NAME.so
