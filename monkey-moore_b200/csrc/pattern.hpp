@@ -27,6 +27,7 @@ struct mmg_program {
     // sizing hints remembered from the previous scan with this pattern (not part of its semantics)
     mutable std::atomic<uint64_t> last_count{0};
     mutable std::atomic<uint64_t> last_events_per_warp{0};
+    mutable std::atomic<uint64_t> last_events{0};          // total events of the previous scan
 
     int value_of(uint32_t c) const;        // code point, or index in char_seq (0 when absent)
 };

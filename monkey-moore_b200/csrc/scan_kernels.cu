@@ -949,6 +949,15 @@ __device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom 
     }
 }
 
+#ifdef MMG_RESOLVE_PROF
+__device__ unsigned long long g_phase_ns[8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PHASE_MARK(k) do { __syncthreads(); if (threadIdx.x == 0) { unsigned long long now_ = gtimer(); atomicAdd(&g_phase_ns[k], now_ - t_prev_); t_prev_ = now_; } } while (0)
+#define PHASE_INIT unsigned long long t_prev_ = gtimer()
+#else
+#define PHASE_MARK(k) do { } while (0)
+#define PHASE_INIT do { } while (0)
+#endif
 #define RESOLVE_THREADS 128
 #define RESOLVE_FAST_J 16u
 
@@ -976,6 +985,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     if (tid == 0) s_bi = MAPS_ONLY ? blockIdx.x : atomicAdd(X.ticket, 1u);
     __syncthreads();
     const uint32_t bi = s_bi;
+    PHASE_INIT;
     const bool bad = events_overflowed(X);
     // segment bi = segment (bi mod segs_per_block) of engine block (bi / segs_per_block)
     const uint32_t rb = bi / G.segs_per_block, si = bi - rb * G.segs_per_block;
@@ -1002,6 +1012,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 for (uint32_t c = 0; c < npads; c++) s_phase[c] = lattice_advance(s_phase[c], nvalid * NP, J0);
             continue;
         }
+        PHASE_MARK(0);
         // (a) maps of this thread's sub-tile, both alignment classes
         uint32_t n = 0;
         uint32_t *ev = nullptr;
@@ -1084,6 +1095,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             }
             return;
         }
+        PHASE_MARK(1);
         // (b) phases: warp c composes the maps of class c over the sub-tiles of this round, in order
         if (wid < (int)npads) {
             const uint32_t c = wid;
@@ -1103,6 +1115,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             if (lane == 0) s_phase[c] = ph;
         }
         __syncthreads();
+        PHASE_MARK(2);
         // (c) replay the true chains through this thread's events
         uint32_t cnt = 0;
         if (he && fast) {
@@ -1159,6 +1172,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 
     if (MAPS_ONLY) return;       // (an overflowed event buffer skips the loop: nothing to do, the resolve kernel reports it)
 
+    PHASE_MARK(3);
     // (d) base of this block in the output: decoupled look-back, 8 x 32 predecessors per step (the eight
     // window loads are independent, so a block far from the nearest inclusive prefix still needs few round trips)
     if (wid == 0) {
@@ -1199,6 +1213,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     }
     __syncthreads();
 
+    PHASE_MARK(4);
     // (e) ordered emission
     if (total != 0) {
         uint64_t running = s_before;
@@ -1224,6 +1239,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         }
     }
 
+    PHASE_MARK(5);
     // (f) the last CTA to finish hands the status words to the host (pinned, device-visible slot) and restores the
     // all-zero state of the workspace, so the next scan on this stream needs no memset and no status copy
     __shared__ uint32_t s_last;
@@ -1579,3 +1595,11 @@ cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, c
     g_merge<<<(unsigned)((chains + 127) / 128), 128, 0, stream>>>(nblocks, counts, bases, in_off, in_val, out_off, out_val);
     return cudaGetLastError();
 }
+
+#ifdef MMG_RESOLVE_PROF
+extern "C" void mmg_debug_resolve_phases(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_ns, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_ns, z, sizeof(z)); }
+}
+#endif

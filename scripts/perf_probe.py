@@ -36,3 +36,12 @@ for name, bits, pat, buf, be in cases:
     gbf = size / best["ms_filter"] / 1e6
     print(f"{name:16s} matches={n:9d} events={best['events']:10d} total={best['ms_total']:8.3f} ms ({gbs:7.1f} GB/s) "
           f"filter={best['ms_filter']:8.3f} ms ({gbf:7.1f} GB/s) launches={best['launches']}", flush=True)
+    if name.startswith("8 abc low16"):
+        import time
+        r = prog.engine_scan(buf, 524288)
+        r.count
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        u = r.unique_indices()
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        print(f"   distinct tables: {len(u)} of {r.count} matches in {(t1 - t0) * 1e3:.3f} ms (mmg_results_unique, host call)")
+        r.close()
