@@ -934,18 +934,36 @@ __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint
 
 template <int W, bool BE>
 __device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t t,
-                                             uint64_t at, uint64_t *out_off, uint32_t *out_val) {
+                                             uint64_t at, uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_val) {
     const uint32_t n = X.sub_count[t];
-    const uint32_t *ev = X.ev + X.sub_start[t];
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t w = ev[i];
-        if (!(w & MMG_EV_VISITED)) continue;
-        const uint64_t s = ((uint64_t)t << MMG_SUBTILE_SHIFT) + MMG_EV_OFF(w);
-        out_off[at] = (G.base_offset + s) >> G.report_shift;
-        const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
-        const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
-        out_val[at] = v0 | (v1 << 16);
-        at++;
+    const uint32_t *__restrict__ ev = X.ev + X.sub_start[t];
+    const uint8_t *__restrict__ data = G.data;
+    const uint32_t o0 = (uint32_t)P.first_lit * W;
+    const bool has1 = P.opp_idx >= 0;
+    const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
+    const uint64_t tbase = (uint64_t)t << MMG_SUBTILE_SHIFT;
+    // eight events at a time: their words, then the element loads of the visited ones (independent of each other: one
+    // memory round trip per batch instead of one per match), then the stores
+    for (uint32_t i0 = 0; i0 < n; i0 += 8) {
+        uint32_t w[8], v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = i0 + k < n ? ev[i0 + k] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = 0;
+            if (w[k] & MMG_EV_VISITED) {
+                const uint64_t s = tbase + MMG_EV_OFF(w[k]);
+                v[k] = ld_elem<W, BE>(data + s + o0);
+                if (has1) v[k] |= ld_elem<W, BE>(data + s + o1) << 16;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (w[k] & MMG_EV_VISITED) {
+                out_off[at] = (G.base_offset + tbase + MMG_EV_OFF(w[k])) >> G.report_shift;
+                out_val[at] = v[k];
+                at++;
+            }
     }
 }
 
@@ -1036,15 +1054,25 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     s_E[(c * RESOLVE_FAST_J + ry) * RESOLVE_THREADS + tid] + ((w >> 16) & 0x100u);
                 seen |= 1u << c;
             };
-            uint32_t i = n;
-            for (; i >= 8; i -= 8) {        // eight independent loads in flight per thread, then the dependent updates
-                uint32_t w8[8];
+            // right to left, eight events per batch; the next batch is requested before the current one is applied, so the
+            // memory round trips of a long event list overlap with the dependent shared-memory updates
+            {
+                uint32_t cur[8], nxt[8];
+                uint32_t i = n;
 #pragma unroll
-                for (int k = 0; k < 8; k++) w8[k] = ev[i - 1 - k];
+                for (int k = 0; k < 8; k++) cur[k] = (uint32_t)k < i ? ev[i - 1 - k] : 0u;
+                while (i > 0) {
+                    const uint32_t ni = i > 8 ? i - 8 : 0u;
 #pragma unroll
-                for (int k = 0; k < 8; k++) step(w8[k]);
+                    for (int k = 0; k < 8; k++) nxt[k] = (uint32_t)k < ni ? ev[ni - 1 - k] : 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if ((uint32_t)k < i) step(cur[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+                    i = ni;
+                }
             }
-            while (i-- > 0) step(ev[i]);
             s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
         } else if (he) {
             n = X.sub_count[t];
@@ -1139,15 +1167,18 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                         xm[c] = r + j >= J0 ? r + j - J0 : r + j;
                     }
                 };
-                uint32_t i = 0;
-                for (; i + 8 <= n; i += 8) {
-                    uint32_t w8[8];
+                uint32_t cur[8], nxt[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) w8[k] = ev[i + k];
+                for (int k = 0; k < 8; k++) cur[k] = (uint32_t)k < n ? ev[k] : 0u;
+                for (uint32_t i = 0; i < n; i += 8) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) visit(i + k, w8[k]);
+                    for (int k = 0; k < 8; k++) nxt[k] = i + 8 + k < n ? ev[i + 8 + k] : 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (i + k < n) visit(i + k, cur[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cur[k] = nxt[k];
                 }
-                for (; i < n; i++) visit(i, ev[i]);
             }
             X.mcount[t] = cnt;
         } else if (he) {
