@@ -344,8 +344,11 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     CU(mmg_filter_occupancy(W, t.lag_bytes, rq.big_endian, P.nkeys, &occ));
     t.grid = dev.sms * std::max(occ, 1);
     t.total_warps = (uint64_t)t.grid * 8;
-    uint32_t cs = 8;   // sub-tiles per chunk: small enough that dynamic scheduling balances the tail
-    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < 8 * t.total_warps)) cs >>= 1;
+    // sub-tiles per chunk: small enough that dynamic scheduling balances the tail (at least 4 chunks per warp;
+    // MMG_CHUNKS_PER_WARP overrides), large enough that the u16 queue entries of k_filter can address the chunk (<= 8 sub-tiles + halo)
+    static const uint64_t per_warp_min = getenv("MMG_CHUNKS_PER_WARP") ? (uint64_t)atoi(getenv("MMG_CHUNKS_PER_WARP")) : 4;
+    uint32_t cs = 8;
+    while (cs > 1 && (spb % cs != 0 || nsub64 / cs < per_warp_min * t.total_warps)) cs >>= 1;
     G.chunk_subs = cs;
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
 

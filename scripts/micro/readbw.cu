@@ -90,6 +90,56 @@ __global__ void __launch_bounds__(256) k_tma(const uint8_t *p, uint64_t n, uint3
     if (acc == 0x12345678u) out[0] = acc;
 }
 
+// (3) dynamic draws like mode 0, but the NEXT chunk is drawn when the current one starts (the atomic's latency hides
+// behind the current chunk) and the ring keeps running across the chunk boundary (no drain / refill per chunk)
+template <int STAGE, int NST>
+__global__ void __launch_bounds__(256) k_tma3(const uint8_t *p, uint64_t n, uint32_t CH, unsigned long long *ctr, uint32_t *out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t *ring = smem + (size_t)wib * (NST * STAGE + 64);
+    const uint32_t ring_a = smem_u32(ring), bar_a = ring_a + NST * STAGE;
+    if (lane == 0) { for (int i = 0; i < NST; i++) mbar_init(bar_a + 8 * i, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    uint32_t acc = 0, slot = 0, parity = 0;
+    const uint32_t nchunks = (uint32_t)(n / CH), nst = CH / STAGE;
+    uint32_t c = 0;
+    if (lane == 0) c = (uint32_t)atomicAdd(ctr, 1ull);
+    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+    if (c >= nchunks) return;
+    uint32_t nxt_reg = 0;
+    if (lane == 0) nxt_reg = (uint32_t)atomicAdd(ctr, 1ull);
+    if (lane == 0)
+        for (uint32_t k = 0; k < nst && k < NST; k++) {
+            mbar_expect_tx(bar_a + 8 * k, STAGE);
+            tma_load_1d(ring_a + k * STAGE, p + (uint64_t)c * CH + (uint64_t)k * STAGE, STAGE, bar_a + 8 * k);
+        }
+    for (;;) {
+        uint32_t nxt = 0xFFFFFFFFu;
+        bool known = false;
+        for (uint32_t k = 0; k < nst; k++) {
+            mbar_wait(bar_a + 8 * slot, parity);
+            for (uint32_t r = 0; r < STAGE / 512; r++) { uint4 v = lds128(ring_a + slot * STAGE + r * 512 + lane * 16); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+            __syncwarp();
+            uint32_t kk = k + NST;
+            uint32_t cc = c;
+            if (kk >= nst) {
+                if (!known) { nxt = __shfl_sync(0xFFFFFFFFu, nxt_reg, 0); known = true; }
+                kk -= nst; cc = nxt;
+            }
+            if (lane == 0 && cc < nchunks) {
+                mbar_expect_tx(bar_a + 8 * slot, STAGE);
+                tma_load_1d(ring_a + slot * STAGE, p + (uint64_t)cc * CH + (uint64_t)kk * STAGE, STAGE, bar_a + 8 * slot);
+            }
+            if (++slot == NST) { slot = 0; parity ^= 1u; }
+        }
+        if (!known) nxt = __shfl_sync(0xFFFFFFFFu, nxt_reg, 0);
+        c = nxt;
+        if (c >= nchunks) break;
+        if (lane == 0) nxt_reg = (uint32_t)atomicAdd(ctr, 1ull);
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
 template <class F> float timeit(F f, int iters = 10) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); f();
@@ -107,6 +157,15 @@ template <int STAGE, int NST, int MODE, int HALO = 0> void run_tma(const uint8_t
     printf("tma mode=%d stage=%5d halo=%d nst=%d chunk=%7u ctas/sm=%d : %.3f ms  %.0f GB/s\n", MODE, STAGE, HALO, NST, CH, occ, ms, n / ms / 1e6);
 }
 
+template <int STAGE, int NST> void run_tma3(const uint8_t *d, uint64_t n, uint32_t CH, int ctas_per_sm, unsigned long long *ctr, uint32_t *out) {
+    const size_t smem = 8 * (NST * STAGE + 64);
+    CK(cudaFuncSetAttribute(k_tma3<STAGE, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tma3<STAGE, NST>, 256, smem);
+    if (occ > ctas_per_sm) occ = ctas_per_sm;
+    float ms = timeit([&] { cudaMemsetAsync(ctr, 0, 8); k_tma3<STAGE, NST><<<148 * occ, 256, smem>>>(d, n, CH, ctr, out); });
+    printf("tma mode=3 (early draw, continuous ring) stage=%5d nst=%d chunk=%7u ctas/sm=%d : %.3f ms  %.0f GB/s\n", STAGE, NST, CH, occ, ms, n / ms / 1e6);
+}
+
 int main(int argc, char **argv) {
     const uint64_t n = (uint64_t)(argc > 1 ? atoi(argv[1]) : 512) << 20;
     uint8_t *d; uint32_t *out; unsigned long long *ctr;
@@ -122,12 +181,11 @@ int main(int argc, char **argv) {
         float ms = timeit([&] { k_ldg<4><<<1, 32>>>((const uint4 *)d, 0, out); });
         printf("empty launch: %.4f ms\n", ms);
     }
-    for (uint32_t ch : {4096u, 8192u, 16384u, 32768u, 65536u}) {
-        run_tma<4096, 2, 0, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
-        run_tma<4096, 2, 2, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
-        run_tma<2048, 3, 0, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
-        run_tma<2048, 3, 2, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
-        run_tma<4096, 2, 1, 16>(d + 4096, n - 8192, ch, 3, ctr, out);
+    for (uint32_t ch : {8192u, 16384u, 32768u}) {
+        run_tma<2048, 3, 0, 0>(d, n, ch, 3, ctr, out);
+        run_tma3<2048, 3>(d, n, ch, 3, ctr, out);
+        run_tma<4096, 2, 0, 0>(d, n, ch, 3, ctr, out);
+        run_tma3<4096, 2>(d, n, ch, 3, ctr, out);
     }
     CK(cudaDeviceSynchronize());
     return 0;
