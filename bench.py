@@ -225,7 +225,16 @@ def run_ours(args, w):
     def step(collect=None):
         return complete_step(enqueue_step(), collect)
 
+    def drain():
+        # Rank 0 completes the gather it only enqueued (header read, receives of lists that overflowed the packed
+        # buffer).  Must happen before any barrier: the other ranks' overflow sends sit on their streams until rank 0
+        # posts the receives, and a barrier behind those sends would wait for a rank 0 that waits in the barrier.
+        g = pending_gather[0]
+        if g is not None:
+            g.counts()
+
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -257,6 +266,7 @@ def run_ours(args, w):
     launches += l
     filt_ms += fm
     filt_bytes += fb
+    drain()                 # the last step's gather completes inside the timed region
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
