@@ -243,14 +243,14 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
       std::ifstream preview_file(config.file_path, std::ios::binary);
       if (!preview_file.is_open())
          throw std::runtime_error("Failed to open file to generate previews: " + config.file_path.string());
-      for (auto &result : results) result.preview = generate_preview(preview_file, file_size, result.offset, result.values_map);
+      for (auto &result : results) result.preview = render_preview(preview_file, file_size, result.offset, result.values_map);
    }
    return results;
 }
 
 template <typename DataType>
-std::string mmoore::SearchEngine<DataType>::generate_preview(std::ifstream &file, uint64_t file_size, uint64_t match_offset,
-                                                             std::map<CharType, DataType> &values_map) {
+std::string mmoore::SearchEngine<DataType>::render_preview(std::ifstream &file, uint64_t file_size, uint64_t match_offset,
+                                                           std::map<CharType, DataType> &values_map) {
    const int64_t elem = static_cast<int64_t>(sizeof(DataType));
    const int64_t width = config.preferred_preview_width;
    // centre the match in the window
@@ -268,12 +268,12 @@ std::string mmoore::SearchEngine<DataType>::generate_preview(std::ifstream &file
    file.read(reinterpret_cast<char *>(window.data()), width * elem);
    window.resize(static_cast<size_t>(file.gcount()) / sizeof(DataType));
    if (sizeof(DataType) > 1) mmoore::adjust_endianness(window.data(), window.size(), config.endianness);
-   return decode_raw_data(values_map, window);
+   return render_window(values_map, window);
 }
 
 template <typename DataType>
-std::string mmoore::SearchEngine<DataType>::decode_raw_data(std::map<CharType, DataType> &values_map,
-                                                            std::vector<DataType> &raw_data) {
+std::string mmoore::SearchEngine<DataType>::render_window(std::map<CharType, DataType> &values_map,
+                                                          std::vector<DataType> &raw_data) {
    std::ostringstream text;
    if (!config.is_relative_search) {
       // value scan: hex dump of the window
