@@ -118,3 +118,24 @@ def test_workload_blobs_are_slice_consistent(mm):
     le, _ = o.engine(whole, w.block_size, big_endian=False)
     be, _ = o.engine(whole, w.block_size, big_endian=True)
     assert len(le) > 0 and len(be) > 0      # planted matches are found in both byte orders
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The bench line the last GPU run produced (profiles/r1_bench_cfg2_n1.json) carries every key of the driver's
+    contract: base keys, roofline, cpu_baseline, e2e, gpu_launches, clocks."""
+    import json
+    path = os.path.join(ROOT, "profiles", "r1_bench_cfg2_n1.json")
+    line = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in line, k
+    assert line["config"]["workload"] == "cfg2" and "model" not in line["config"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in line["roofline"], k
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in line["cpu_baseline"], k
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in line["e2e"], k
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0
+    assert line["parity"]["bit_exact"] is True
