@@ -387,7 +387,7 @@ def run_ours(args, w):
                            "l2": "input (%d MiB per GPU) larger than the 126 MB L2, no flush needed" % (w.size >> 20),
                            "parallelism": "block-sharded x%d" % world},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "kernel": "k_filter" if w.bits == 16 else "k_filter8", "peak_source": peak_src,
+                             "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "kernel": "k_filter" if w.bits == 16 else "k_filter8", "peak_source": peak_src,
                              "timing": "CUDA events around the filter launch on its stream, %d launches run alone "
                                        "after the timed region (inside it scans overlap on two streams)" % alone_n,
                              "achieved_in_timed_region": achieved_overlapped,
