@@ -91,12 +91,17 @@ int main(int argc, char **argv) {
    const bool with_engine = argc > 2 && std::string(argv[2]) == "engine";
    const std::vector<CharType> abcde = {'a', 'b', 'c', 'd', 'e'};
    const std::vector<CharType> front = {'*', 'b', 'c', 'd', 'e'}, middle = {'a', 'b', '*', 'd', 'e'}, end = {'a', 'b', 'c', 'd', '*'};
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint8_t>("BM_Search/Relative/8-Bit", abcde, 0, bytes, budget);
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint16_t>("BM_Search/Relative/16-Bit", abcde, 0, bytes, budget);
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint8_t>("BM_Search/Relative/Wildcard/Front/8-Bit", front, '*', bytes, budget);
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint8_t>("BM_Search/Relative/Wildcard/Middle/8-Bit", middle, '*', bytes, budget);
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint8_t>("BM_Search/Relative/Wildcard/End/8-Bit", end, '*', bytes, budget);
-   for (size_t bytes = 128u << 10; bytes <= (16u << 20); bytes *= 4) run_search<uint16_t>("BM_Search/Relative/Wildcard/Middle/16-Bit", middle, '*', bytes, budget);
+   // ->RangeMultiplier(4)->Range(128<<10, 16<<20): Google Benchmark appends the upper bound, so the rows are
+   // 128 KiB, 512 KiB, 2 MiB, 8 MiB and 16 MiB (benchmarks/bench_search.cpp:67-105 of the reference)
+   const size_t sizes[] = {128u << 10, 512u << 10, 2u << 20, 8u << 20, 16u << 20};
+   for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/8-Bit", abcde, 0, bytes, budget);
+   for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/16-Bit", abcde, 0, bytes, budget);
+   for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/Wildcard/Front/8-Bit", front, '*', bytes, budget);
+   for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/Wildcard/Middle/8-Bit", middle, '*', bytes, budget);
+   for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/Wildcard/Back/8-Bit", end, '*', bytes, budget);
+   for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/Wildcard/Front/16-Bit", front, '*', bytes, budget);
+   for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/Wildcard/Middle/16-Bit", middle, '*', bytes, budget);
+   for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/Wildcard/Back/16-Bit", end, '*', bytes, budget);
    // the BASELINE configs' own patterns (not part of the reference harness)
    const std::vector<CharType> monkey = {'m', 'o', 'n', 'k', 'e', 'y'}, mokeys = {'m', 'o', '*', 'k', 'e', 'y', '*', 's'};
    run_search<uint8_t>("cfg1 8-bit monkey", monkey, 0, 16u << 20, budget);

@@ -143,20 +143,27 @@ int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
  * (src/core/search_engine.cpp:82-102, 193-197); across GPUs ranks scan disjoint block ranges
  * (mmg_engine_scan with first_block/num_blocks) and only the result lists travel.  Rank order equals
  * file order, so the concatenation is already sorted.  NCCL is loaded lazily (dlopen): single-GPU
- * users do not need it.
+ * users do not need it.  All gather work runs on the communicator's own CUDA stream.
  *   mmg_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller broadcasts it (any transport).
  *   mmg_comm_create    : collective over all ranks; capacity = entries of the fixed packed buffer.
  *   mmg_comm_gather    : collective; the `nlists` lists of one step (same nlists on every rank) go to
- *                        rank 0 in ONE grouped NCCL operation (+ point-to-point spill when a rank's lists
- *                        exceed the packed capacity).  *out is non-NULL on rank 0 only.  */
+ *                        rank 0 in ONE grouped NCCL operation (+ point-to-point sends of whatever exceeds
+ *                        the packed capacity; rank 0 posts the matching receives before its call returns,
+ *                        so no send stays unmatched behind the call).  *out is non-NULL on rank 0 only.
+ *                        The lists may be freed right after the call on every rank.
+ *   mmg_comm_wait      : blocks until this rank's part of every gather so far has executed; *ms_last
+ *                        (may be NULL) = device time of the last gather on this rank's gather stream.
+ *   mmg_gathered_pieces: device-resident pieces (rank order == file order) of one gathered list. */
 typedef struct mmg_comm mmg_comm;
 typedef struct mmg_gathered mmg_gathered;
 int mmg_comm_unique_id(void *out128);
 int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, mmg_comm **out);
 void mmg_comm_destroy(mmg_comm *c);
 int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out);
+int mmg_comm_wait(mmg_comm *c, float *ms_last);
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list);
 int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32_t *values);
+int mmg_gathered_pieces(const mmg_gathered *g, int list, const uint64_t **offs, const uint32_t **vals, uint64_t *ns, int cap);
 void mmg_gathered_free(mmg_gathered *g);
 
 /* Page-locked host staging memory for file -> HBM ingestion (SearchEngine<T>::run reads the file into

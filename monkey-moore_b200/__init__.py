@@ -34,8 +34,8 @@ C_ABI_SYMBOLS = [
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_engine_scan_async", "mmg_results_wait", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_unique", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
     "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
-    "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_gathered_count",
-    "mmg_gathered_copy", "mmg_gathered_free",
+    "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_comm_wait",
+    "mmg_gathered_count", "mmg_gathered_copy", "mmg_gathered_pieces", "mmg_gathered_free",
 ]
 
 _u32p = C.POINTER(C.c_uint32)
@@ -107,6 +107,8 @@ def lib():
         l.mmg_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
         l.mmg_comm_destroy.argtypes = [C.c_void_p]
         l.mmg_comm_gather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+        l.mmg_comm_wait.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        l.mmg_gathered_pieces.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _u64p, C.c_int]
         l.mmg_gathered_count.restype = C.c_uint64
         l.mmg_gathered_count.argtypes = [C.c_void_p, C.c_int]
         l.mmg_gathered_copy.argtypes = [C.c_void_p, C.c_int, _u64p, _u32p]
@@ -246,21 +248,28 @@ class Comm:
         self._h = h
 
     def gather(self, results, fetch=False, lazy=False):
-        """Collective.  ``lazy=True`` only enqueues the gather and returns a :class:`Gathered` (rank 0) that
-        completes on first use; otherwise rank 0 gets the per-search counts (or the lists with ``fetch=True``)."""
+        """Collective.  Rank 0 gets the per-search counts (or the lists with ``fetch=True``, or a
+        :class:`Gathered` with ``lazy=True``); the other ranks get ``None``.  The result lists may be closed
+        right after the call on every rank (the library releases them behind the gather's reads)."""
         n = len(results)
         arr = (C.c_void_p * n)(*[r._h for r in results])
         g = C.c_void_p()
         _check(lib().mmg_comm_gather(self._h, arr, n, C.byref(g)))
         if not g:
             return None
-        out = Gathered(g, n, list(results))
+        out = Gathered(g, n)
         if lazy:
             return out
         try:
             return out.fetch() if fetch else out.counts()
         finally:
             out.close()
+
+    def wait(self):
+        """Blocks until this rank's part of every gather so far has executed -> device ms of the last gather."""
+        ms = C.c_float(0)
+        _check(lib().mmg_comm_wait(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -271,10 +280,10 @@ class Comm:
 
 
 class Gathered:
-    """Rank 0's view of one gather.  Keeps the rank's own result lists alive until the gather is complete."""
+    """Rank 0's view of one gather (valid until the next gather on the same communicator)."""
 
-    def __init__(self, handle, nlists, keep):
-        self._h, self.nlists, self._keep = handle, nlists, keep
+    def __init__(self, handle, nlists):
+        self._h, self.nlists = handle, nlists
 
     def counts(self):
         return [int(lib().mmg_gathered_count(self._h, k)) for k in range(self.nlists)]
@@ -289,11 +298,17 @@ class Gathered:
             out.append((off, val))
         return out
 
+    def pieces(self, k):
+        """Device-resident pieces of list k in file order: [(offsets_ptr, values_ptr, n)]."""
+        cap = 1024
+        offs, vals, ns = (C.c_void_p * cap)(), (C.c_void_p * cap)(), (C.c_uint64 * cap)()
+        n = lib().mmg_gathered_pieces(self._h, k, offs, vals, ns, cap)
+        return [(offs[i], vals[i], int(ns[i])) for i in range(min(n, cap))]
+
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.mmg_gathered_free(self._h)
             self._h = None
-            self._keep = None
 
     __del__ = close
 

@@ -16,7 +16,10 @@
 #include "mmoore_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <memory>
@@ -131,6 +134,23 @@ void read_range(int fd, uint64_t lo, uint64_t len, uint8_t *dst) {
    for (auto &t : readers) t.join();
 }
 
+// MMOORE_PROFILE=1: host-side phase times of run() on stderr (development aid; no effect on results)
+struct PhaseClock {
+   bool on = std::getenv("MMOORE_PROFILE") != nullptr;
+   double t[4] = {0, 0, 0, 0};
+   static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+   template <class F> auto time(int k, F &&f) {
+      if (!on) return f();
+      const double t0 = now();
+      struct Stop { double &acc; double t0; ~Stop() { acc += now() - t0; } } stop{t[k], t0};
+      return f();
+   }
+   ~PhaseClock() {
+      if (on) std::fprintf(stderr, "[mmoore] run(): take/pin %.2f ms  read %.2f ms  enqueue %.2f ms  collect %.2f ms\n",
+                           1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3]);
+   }
+};
+
 struct FileDescriptor {
    int fd;
    explicit FileDescriptor(const std::filesystem::path &p) : fd(::open(p.c_str(), O_RDONLY)) {}
@@ -215,24 +235,27 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
          return true;
       };
 
+      PhaseClock clock;
       uint64_t k = 0;
       for (uint64_t first = 0; first < num_blocks; first += blocks_per_slab, k++) {
          Slot &slot = slots[k & 1];
-         if (slot.res && !collect(slot)) return {};          // slab k-2 used this buffer
+         if (slot.res && !clock.time(3, [&] { return collect(slot); })) return {};          // slab k-2 used this buffer
          if (abort_flag) return {};
-         if (!slot.buf) slot.buf = staging_pool().take(slab_capacity);
+         if (!slot.buf) clock.time(0, [&] { slot.buf = staging_pool().take(slab_capacity); return 0; });
          const uint64_t n = std::min<uint64_t>(blocks_per_slab, num_blocks - first);
          const uint64_t lo = first * block;
          const uint64_t hi = std::min<uint64_t>(file_size, (first + n) * static_cast<uint64_t>(block) + overlap);
-         read_range(file.fd, lo, hi - lo, slot.buf->ptr);
-         const int rc = mmg_engine_scan_async(searcher->program(), slot.buf->ptr, hi - lo, MMG_MEM_HOST, file_size, block,
-                                              first, n, big_endian ? 1 : 0, &slot.res);
+         clock.time(1, [&] { read_range(file.fd, lo, hi - lo, slot.buf->ptr); return 0; });
+         const int rc = clock.time(2, [&] {
+            return mmg_engine_scan_async(searcher->program(), slot.buf->ptr, hi - lo, MMG_MEM_HOST, file_size, block, first, n,
+                                         big_endian ? 1 : 0, &slot.res);
+         });
          if (rc != MMG_OK) throw_last(rc);
          slot.blocks = n;
       }
       // the last two slabs, oldest first
       for (uint64_t j = k >= 2 ? k - 2 : 0; j < k; j++)
-         if (slots[j & 1].res && !collect(slots[j & 1])) return {};
+         if (slots[j & 1].res && !clock.time(3, [&] { return collect(slots[j & 1]); })) return {};
    }
    if (abort_flag) return {};
 

@@ -42,8 +42,8 @@ int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everythi
 thread_local cudaStream_t g_user_stream = nullptr;   // set by mmg_set_stream: scans run on the caller's stream
 thread_local bool g_use_user_stream = false;
 
-// Per (host thread, device) scan workspace, reused by every tiled scan: nothing is allocated, zeroed or copied per
-// scan in the steady state.  `zero` holds the state that must be all-zero when a scan starts (status words, tickets,
+// Per (device, lane) scan workspace, reused by every tiled scan: nothing is allocated, zeroed or copied per scan in
+// the steady state.  `zero` holds the state that must be all-zero when a scan starts (status words, tickets,
 // look-back words); the resolve kernel restores it when it ends.  Scans on one stream execute in order, so sharing the
 // workspace between scans that are enqueued back to back is safe; `generation` tells a pending scan whether its
 // scratch contents (needed only for the exact re-emission) are still there.
@@ -65,38 +65,52 @@ struct Lane {
     Workspace ws;
 };
 
+// PROCESS-WIDE state of one device: streams, lanes and their workspaces are created once and shared by every host
+// thread (the reference GUI starts a fresh thread per search, src/gui/monkey_frame.cpp:1167 -- per-thread state would
+// leak streams and workspaces with every search).  `mu` serialises the enqueue side: the order in which scans reach a
+// lane's stream is the order in which they use its workspace.  Objects live until the process exits, so the
+// Workspace pointer a pending scan keeps stays valid whichever thread completes or frees it.
 struct DeviceInfo {
     int device = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;       // the caller's stream (mmg_set_stream) or own_stream: scans are ordered after it
-    cudaStream_t own_stream = nullptr;   // this library's non-blocking stream
+    cudaStream_t own_stream = nullptr;   // this library's non-blocking stream (callers without mmg_set_stream)
     Lane lanes[2];
     unsigned next_lane = 0;
+    std::mutex mu;
 };
 
-// one stream per host thread and device
+std::mutex g_devices_mutex;
+std::deque<DeviceInfo> g_devices;        // deque: stable addresses
+
 DeviceInfo &device_info() {
-    thread_local std::deque<DeviceInfo> infos;      // deque: pending scans keep pointers to their workspace
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) throw ScanError{fail(MMG_ERR_CUDA, "no usable CUDA device")};
-    for (auto &d : infos)
-        if (d.device == dev) { d.stream = g_use_user_stream ? g_user_stream : d.own_stream; return d; }
-    DeviceInfo d;
-    d.device = dev;
-    CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-    CU(cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
-    for (Lane &l : d.lanes) {
-        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    std::lock_guard<std::mutex> lock(g_devices_mutex);
+    for (auto &d : g_devices)
+        if (d.device == dev) return d;
+    g_devices.emplace_back();
+    DeviceInfo &d = g_devices.back();
+    try {
+        CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
+        for (Lane &l : d.lanes) {
+            CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        }
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;   // keep freed scratch in the pool: steady-state scans do not hit cudaMalloc
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    } catch (...) {
+        g_devices.pop_back();
+        throw;
     }
-    d.stream = g_use_user_stream ? g_user_stream : d.own_stream;
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;   // keep freed scratch in the pool: steady-state scans do not hit cudaMalloc
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    infos.push_back(d);
-    return infos.back();
+    d.device = dev;
+    return d;
 }
+
+// the stream scans of the calling thread are ordered after: its mmg_set_stream stream, or the library's own
+cudaStream_t caller_stream(DeviceInfo &d) { return g_use_user_stream ? g_user_stream : d.own_stream; }
 
 // stream-ordered scratch that is released when the scan ends
 struct Arena {
@@ -141,6 +155,8 @@ struct mmg_results {
     uint64_t *d_off = nullptr;    // one allocation: offsets, then values
     uint32_t *d_val = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t free_stream = nullptr;   // non-null: release the lists in this stream's order (a gather still reads them there)
+    DeviceInfo *dev = nullptr;            // process-wide device state the scan was enqueued on
     mmg_scan_stats stats{};
     // ---- in-flight state (mmg_*_async): completed by finish_scan()
     bool pending = false;
@@ -375,8 +391,11 @@ void finish_tiled(mmg_results *res) {
         if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
         t.per_warp = status[0] + status[0] / 4 + 64;
         if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
-        enqueue_tiled(res);
-        CU(cudaEventRecord(res->ev[3], stream));
+        {
+            std::lock_guard<std::mutex> lock(res->dev->mu);
+            enqueue_tiled(res);
+            CU(cudaEventRecord(res->ev[3], stream));
+        }
         CU(cudaStreamSynchronize(stream));
     }
     res->rq.prog->last_events_per_warp = status[0];
@@ -387,16 +406,19 @@ void finish_tiled(mmg_results *res) {
     if (res->count > t.cap) {
         // the optimistic buffer was too small: allocate exactly and emit again from the stored bases -- or, when
         // another scan has used the workspace since, run the whole scan again
-        free_results(res);
-        t.cap = res->count;
-        alloc_results(res, t.cap);
-        if (t.generation == t.ws->generation) {
-            CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
-            res->launches += 1;
-        } else {
-            enqueue_tiled(res);
+        {
+            std::lock_guard<std::mutex> lock(res->dev->mu);
+            free_results(res);
+            t.cap = res->count;
+            alloc_results(res, t.cap);
+            if (t.generation == t.ws->generation) {
+                CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
+                res->launches += 1;
+            } else {
+                enqueue_tiled(res);
+            }
+            CU(cudaEventRecord(res->ev[3], stream));
         }
-        CU(cudaEventRecord(res->ev[3], stream));
         CU(cudaStreamSynchronize(stream));
     }
 }
@@ -431,6 +453,8 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         static const int ndev = [] { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; } return n; }();
         if (ndev == 0) throw ScanError{fail(MMG_ERR_CUDA, "no CUDA device: this library has no CPU fallback")};
         DeviceInfo &dev = device_info();
+        res->dev = &dev;
+        std::lock_guard<std::mutex> lock(dev.mu);             // enqueue order == workspace order (see DeviceInfo)
         // Consecutive scans alternate between two stream lanes so that the (tiny) resolve kernel of a sparse scan runs
         // beside the next filter kernel.  A scan with millions of events has a resolve kernel that wants the whole GPU:
         // behind a persistent filter grid it would only start when that grid drains, so such scans stay on one lane
@@ -441,7 +465,7 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         res->stream = stream;
         res->stats.bytes_scanned = nbytes;
         if (nbytes == 0 || nblocks == 0) { *out = res; return MMG_OK; }
-        CU(cudaEventRecord(lane.fork, dev.stream));           // everything the caller enqueued so far (the input!) comes first
+        CU(cudaEventRecord(lane.fork, caller_stream(dev)));           // everything the caller enqueued so far (the input!) comes first
         CU(cudaStreamWaitEvent(stream, lane.fork, 0));
         for (auto &e : res->ev) e = take_event();
         res->status_host = take_slot();
@@ -662,27 +686,24 @@ int mmg_results_unique(const mmg_program *p, const mmg_results *r, uint64_t *ind
         firsts.push_back(0);
     } else {
         cudaStream_t stream = r->stream;
+        if (keymask != 0xFFFFu && p->elem_bits != 8 && M >= 0xFFFFFFFFull)
+            return fail(MMG_ERR_NOMEM, "match list too long for the hashed unique-table pass");
         try {
+            Arena tmp(stream);                      // temporaries are released on every path, error paths included
             if (keymask == 0xFFFFu || p->elem_bits == 8) {
-                uint64_t *d_first = nullptr;
-                CU(cudaMallocAsync((void **)&d_first, 65536 * sizeof(uint64_t), stream));
+                uint64_t *d_first = tmp.get<uint64_t>(65536);
                 CU(cudaMemsetAsync(d_first, 0xFF, 65536 * sizeof(uint64_t), stream));
                 CU(mmg_launch_unique_direct(r->d_val, M, keymask, keymask != 0xFFFFu, d_first, stream));
                 std::vector<uint64_t> table(65536);
                 CU(cudaMemcpyAsync(table.data(), d_first, 65536 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-                CU(cudaFreeAsync(d_first, stream));
                 CU(cudaStreamSynchronize(stream));
                 for (uint64_t v : table)
                     if (v != ~0ull) firsts.push_back(v);
             } else {
-                if (M >= 0xFFFFFFFFull) return fail(MMG_ERR_NOMEM, "match list too long for the hashed unique-table pass");
                 uint64_t cap = 1024;
                 while (cap < 2 * M && cap < (1ull << 28)) cap <<= 1;
-                uint64_t *d_slots = nullptr, *d_out = nullptr, *d_cnt = nullptr;
                 const uint64_t out_cap = std::min<uint64_t>(M, cap);
-                CU(cudaMallocAsync((void **)&d_slots, cap * sizeof(uint64_t), stream));
-                CU(cudaMallocAsync((void **)&d_out, out_cap * sizeof(uint64_t), stream));
-                CU(cudaMallocAsync((void **)&d_cnt, 2 * sizeof(uint64_t), stream));
+                uint64_t *d_slots = tmp.get<uint64_t>(cap), *d_out = tmp.get<uint64_t>(out_cap), *d_cnt = tmp.get<uint64_t>(2);
                 CU(cudaMemsetAsync(d_slots, 0xFF, cap * sizeof(uint64_t), stream));
                 CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(uint64_t), stream));
                 CU(mmg_launch_unique_hash(r->d_val, M, d_slots, (uint32_t)(cap - 1), reinterpret_cast<unsigned int *>(d_cnt + 1), stream));
@@ -690,17 +711,12 @@ int mmg_results_unique(const mmg_program *p, const mmg_results *r, uint64_t *ind
                 uint64_t h_cnt[2] = {0, 0};
                 CU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
                 CU(cudaStreamSynchronize(stream));
-                const bool overflow = (h_cnt[1] & 0xFFFFFFFFull) != 0;
-                if (!overflow) {
-                    firsts.resize(std::min<uint64_t>(h_cnt[0], out_cap));
-                    if (!firsts.empty())
-                        CU(cudaMemcpyAsync(firsts.data(), d_out, firsts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-                }
-                CU(cudaFreeAsync(d_slots, stream));
-                CU(cudaFreeAsync(d_out, stream));
-                CU(cudaFreeAsync(d_cnt, stream));
+                if ((h_cnt[1] & 0xFFFFFFFFull) != 0)
+                    throw ScanError{fail(MMG_ERR_NOMEM, "more distinct tables than the hashed unique-table pass can hold")};
+                firsts.resize(std::min<uint64_t>(h_cnt[0], out_cap));
+                if (!firsts.empty())
+                    CU(cudaMemcpyAsync(firsts.data(), d_out, firsts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
                 CU(cudaStreamSynchronize(stream));
-                if (overflow) return fail(MMG_ERR_NOMEM, "more distinct tables than the hashed unique-table pass can hold");
             }
         } catch (const ScanError &e) {
             cudaGetLastError();
@@ -720,7 +736,9 @@ const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? don
 void mmg_results_free(mmg_results *r) {
     if (!r) return;
     if (r->pending) finish_scan(r);
-    if (r->d_off) cudaFreeAsync(r->d_off, r->stream);      // one allocation: offsets, then values
+    // one allocation: offsets, then values.  A gather that still reads the lists on its own stream has redirected
+    // the release to that stream (mmg_internal_results_free_on): the allocator then cannot recycle them early.
+    if (r->d_off) cudaFreeAsync(r->d_off, r->free_stream ? r->free_stream : r->stream);
     delete r;
 }
 
@@ -733,8 +751,8 @@ int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out) {
     out->d_val = r ? r->d_val : nullptr;
     return MMG_OK;
 }
-void *mmg_internal_stream(void) {
-    try { return device_info().stream; } catch (const ScanError &) { return nullptr; }
+void mmg_internal_results_free_on(const mmg_results *r, void *stream) {
+    if (r) const_cast<mmg_results *>(r)->free_stream = static_cast<cudaStream_t>(stream);
 }
 void mmg_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 
@@ -756,9 +774,9 @@ int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t fi
     if ((nbytes & 7u) || (first_byte & 7u) || (reinterpret_cast<uintptr_t>(device_ptr) & 7u))
         return fail(MMG_ERR_ARG, "mmg_synth_fill works on 8-byte aligned ranges");
     try {
-        DeviceInfo &dev = device_info();
-        CU(mmg_launch_synth(static_cast<uint64_t *>(device_ptr), nbytes / 8, seed, first_byte / 8, byte_mask, dev.stream));
-        CU(cudaStreamSynchronize(dev.stream));
+        cudaStream_t stream = caller_stream(device_info());
+        CU(mmg_launch_synth(static_cast<uint64_t *>(device_ptr), nbytes / 8, seed, first_byte / 8, byte_mask, stream));
+        CU(cudaStreamSynchronize(stream));
     } catch (const ScanError &e) {
         return e.code;
     }

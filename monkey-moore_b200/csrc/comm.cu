@@ -4,11 +4,21 @@
 // (/root/reference/src/core/search_engine.cpp:104-172): nothing is exchanged between blocks, the
 // results are concatenated and sorted (:193-197).  Across GPUs the same holds -- ranks scan
 // disjoint block ranges with no data-path collective -- so the one communication step is this
-// gather.  It is ONE grouped NCCL operation per call: every rank packs the lists of a step into a
-// fixed-capacity buffer [counts | offsets ...] (+ a parallel buffer of table base values) and
-// sends it to rank 0; a rank whose lists do not fit sends the remainder point-to-point, which
-// rank 0 learns from the gathered header.  NCCL is loaded with dlopen so that single-GPU users
-// (the GUI drop-in) need no NCCL installation.
+// gather.  Protocol of one mmg_comm_gather call (a collective):
+//
+//   1. every rank packs the lists of the step into a fixed-capacity buffer [counts | offsets ...]
+//      (+ a parallel buffer of table base values) and ONE grouped NCCL send/recv moves the packed
+//      buffers to rank 0;
+//   2. a rank whose lists do not fit enqueues point-to-point sends of the remainder right behind
+//      the packed send;
+//   3. rank 0 reads the gathered headers INSIDE the call (one small D2H + event wait) and posts the
+//      matching receives before it returns -- a pending send never outlives the call that caused it,
+//      so no later collective (of this or any other communicator) can queue behind an unmatched send.
+//
+// Everything runs on the communicator's OWN stream: the scan streams never wait for NCCL, and a
+// list that is still being read by a send is released in gather-stream order (the results object is
+// told to free itself on this stream), so the stream-ordered allocator cannot recycle it early.
+// NCCL is loaded with dlopen so that single-GPU users (the GUI drop-in) need no NCCL installation.
 #include "../../include/mmoore_b200.h"
 
 #include <cuda_runtime.h>
@@ -23,7 +33,7 @@
 // from capi.cu
 struct mmg_results_view { uint64_t count; const uint64_t *d_off; const uint32_t *d_val; };
 extern "C" int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out);
-extern "C" void *mmg_internal_stream(void);
+extern "C" void mmg_internal_results_free_on(const mmg_results *r, void *stream);
 extern "C" void mmg_internal_set_error(const char *msg);
 
 namespace {
@@ -75,20 +85,22 @@ int err(int code, const std::string &msg) {
         if (e_ != cudaSuccess) return err(MMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-}  // namespace
+const int HDR = 64;      // header entries per rank (list counts); nlists <= 60
 
-struct mmg_gathered;
+}  // namespace
 
 struct mmg_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    uint64_t cap = 0;            // entries per packed buffer (header included)
+    uint64_t cap = 0;               // entries per packed buffer (header included)
+    cudaStream_t stream = nullptr;  // every copy and NCCL call of the gather runs here
+    cudaEvent_t t0 = nullptr, t1 = nullptr, hdr_ready = nullptr;   // device time of the last gather; headers landed
+    bool timed = false;
     uint64_t *pack_off = nullptr;
     uint32_t *pack_val = nullptr;
     uint64_t *recv_off = nullptr;   // rank 0: world * cap
     uint32_t *recv_val = nullptr;
-    uint64_t *hdr_host = nullptr;   // pinned, rank 0: the headers of all ranks (64 entries per rank)
-    mmg_gathered *inflight = nullptr;   // rank 0: a gather whose headers have not been read yet
+    uint64_t *hdr_host = nullptr;   // pinned, rank 0: the headers of all ranks (HDR entries per rank)
 };
 
 struct mmg_gathered {
@@ -97,63 +109,31 @@ struct mmg_gathered {
     // device pieces per list in rank order: (pointer, n) pairs into recv buffers / spill buffers
     struct Piece { const uint64_t *off; const uint32_t *val; uint64_t n; };
     std::vector<std::vector<Piece>> pieces;
-    std::vector<void *> owned;                    // spill buffers to free
-    // deferred completion (rank 0): headers are read and spills received on first use
-    bool pending = false;
-    mmg_comm *comm = nullptr;
+    std::vector<void *> owned;                    // spill buffers (stream-ordered allocations on the gather stream)
     cudaStream_t stream = nullptr;
-    cudaEvent_t ready = nullptr;                  // headers have landed in hdr_host
-    std::vector<mmg_results_view> own;            // rank 0's own lists (their overflow is copied on completion)
-    int error = MMG_OK;
+    cudaEvent_t landed = nullptr;                 // every piece has arrived on rank 0
+    bool waited = false;
 };
 
 namespace {
 
-// rank 0: read the gathered headers, build the piece lists, receive what did not fit into the packed buffers
-int finish_gather(mmg_gathered *g) {
-    if (!g->pending) return g->error;
-    g->pending = false;
-    mmg_comm *c = g->comm;
-    if (c->inflight == g) c->inflight = nullptr;
-    cudaStream_t stream = g->stream;
-    const int nlists = g->nlists;
-    const uint64_t room = c->cap - (uint64_t)nlists;
-    auto bail = [&](int code) { g->error = code; return code; };
-    if (cudaEventSynchronize(g->ready) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "waiting for the gathered headers failed"));
-    cudaEventDestroy(g->ready);
-    g->ready = nullptr;
-    const uint64_t *all = c->hdr_host;
-    bool spilled = false;
-    for (int r = 0; r < c->world; r++) {
-        uint64_t pos = nlists, used_r = 0;
-        for (int k = 0; k < nlists; k++) {
-            const uint64_t n = all[(size_t)r * 64 + k];
-            const uint64_t f = std::min<uint64_t>(n, room - used_r);
-            g->counts[k] += n;
-            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
-            pos += f; used_r += f;
-            if (f < n) {
-                const uint64_t rest = n - f;
-                uint64_t *so; uint32_t *sv;
-                if (cudaMalloc((void **)&so, rest * sizeof(uint64_t)) != cudaSuccess ||
-                    cudaMalloc((void **)&sv, rest * sizeof(uint32_t)) != cudaSuccess)
-                    return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
-                g->owned.push_back(so); g->owned.push_back(sv);
-                if (r == 0) {
-                    if (cudaMemcpyAsync(so, g->own[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
-                        cudaMemcpyAsync(sv, g->own[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
-                        return bail(err(MMG_ERR_CUDA, "copying rank 0's overflow failed"));
-                } else {
-                    if (nccl().Recv(so, rest, ncclUint64, r, c->comm, stream) != ncclSuccess ||
-                        nccl().Recv(sv, rest, ncclUint32, r, c->comm, stream) != ncclSuccess)
-                        return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
-                }
-                g->pieces[k].push_back({so, sv, rest});
-                spilled = true;
-            }
-        }
-    }
-    if (spilled && cudaStreamSynchronize(stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "spill transfer failed"));
+void destroy_comm(mmg_comm *c) {
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
+    if (c->hdr_host) cudaFreeHost(c->hdr_host);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->hdr_ready) cudaEventDestroy(c->hdr_ready);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int wait_landed(mmg_gathered *g) {
+    if (g->waited) return MMG_OK;
+    if (cudaEventSynchronize(g->landed) != cudaSuccess) return err(MMG_ERR_CUDA, "waiting for the gathered lists failed");
+    g->waited = true;
     return MMG_OK;
 }
 
@@ -172,61 +152,65 @@ int mmg_comm_unique_id(void *out128) {
 
 int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, mmg_comm **out) {
     if (!out || !id128 || rank < 0 || rank >= world) return err(MMG_ERR_ARG, "bad communicator arguments");
+    *out = nullptr;
     if (!nccl().ok) return err(MMG_ERR_CUDA, "NCCL library not available (dlopen libnccl.so.2 failed)");
     mmg_comm *c = new mmg_comm();
-    c->rank = rank; c->world = world; c->cap = std::max<uint64_t>(capacity, 64);
+    c->rank = rank; c->world = world; c->cap = std::max<uint64_t>(capacity, 2 * HDR);
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
-    NC(nccl().CommInitRank(&c->comm, world, id, rank));
-    CUC(cudaMalloc((void **)&c->pack_off, c->cap * sizeof(uint64_t)));
-    CUC(cudaMalloc((void **)&c->pack_val, c->cap * sizeof(uint32_t)));
-    if (rank == 0) {
-        CUC(cudaMalloc((void **)&c->recv_off, (size_t)world * c->cap * sizeof(uint64_t)));
-        CUC(cudaMalloc((void **)&c->recv_val, (size_t)world * c->cap * sizeof(uint32_t)));
-    }
-    CUC(cudaHostAlloc((void **)&c->hdr_host, (size_t)world * 64 * sizeof(uint64_t), cudaHostAllocDefault));
+    auto build = [&]() -> int {
+        NC(nccl().CommInitRank(&c->comm, world, id, rank));
+        CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreate(&c->t0));
+        CUC(cudaEventCreate(&c->t1));
+        CUC(cudaEventCreateWithFlags(&c->hdr_ready, cudaEventDisableTiming));
+        CUC(cudaMalloc((void **)&c->pack_off, c->cap * sizeof(uint64_t)));
+        CUC(cudaMalloc((void **)&c->pack_val, c->cap * sizeof(uint32_t)));
+        if (rank == 0) {
+            CUC(cudaMalloc((void **)&c->recv_off, (size_t)world * c->cap * sizeof(uint64_t)));
+            CUC(cudaMalloc((void **)&c->recv_val, (size_t)world * c->cap * sizeof(uint32_t)));
+        }
+        CUC(cudaHostAlloc((void **)&c->hdr_host, (size_t)world * HDR * sizeof(uint64_t), cudaHostAllocDefault));
+        return MMG_OK;
+    };
+    const int rc = build();
+    if (rc != MMG_OK) { destroy_comm(c); return rc; }
     *out = c;
     return MMG_OK;
 }
 
-void mmg_comm_destroy(mmg_comm *c) {
-    if (!c) return;
-    if (c->inflight) finish_gather(c->inflight);
-    if (c->comm) nccl().CommDestroy(c->comm);
-    cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
-    cudaFreeHost(c->hdr_host);
-    delete c;
-}
+void mmg_comm_destroy(mmg_comm *c) { destroy_comm(c); }
 
 // Gathers `nlists` result lists (the searches of one step) of every rank to rank 0.
 // On rank 0 *out receives the gathered lists (rank order == ascending file offsets); elsewhere NULL.
-// The call only ENQUEUES work on the scan stream; rank 0 completes it (header read, spill receives) when
-// the gathered object is first used or freed.  If rank 0's own lists may overflow the packed buffer they
-// must stay alive until then.
+// Blocks the HOST of rank 0 until the packed buffers of all ranks have arrived (their headers size the
+// receives of whatever did not fit); the other ranks only enqueue.  The scan streams are never involved.
 int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out) {
-    if (!c || !lists || nlists <= 0 || nlists > 60 || !out) return err(MMG_ERR_ARG, "bad gather arguments");
+    if (!c || !lists || nlists <= 0 || nlists > HDR - 4 || !out) return err(MMG_ERR_ARG, "bad gather arguments");
     *out = nullptr;
-    if (c->inflight) finish_gather(c->inflight);          // its headers live in the buffer we are about to reuse
-    cudaStream_t stream = static_cast<cudaStream_t>(mmg_internal_stream());
+    cudaStream_t stream = c->stream;
     const uint64_t room = c->cap - (uint64_t)nlists;
     std::vector<mmg_results_view> v(nlists);
-    for (int k = 0; k < nlists; k++) mmg_internal_results_view(lists[k], &v[k]);
+    for (int k = 0; k < nlists; k++) mmg_internal_results_view(lists[k], &v[k]);      // completes the scans: counts are final
 
-    // pack: header (counts) + as much of every list as fits
-    uint64_t hdr[64];
+    CUC(cudaEventRecord(c->t0, stream));
+    // pack: header (counts) + as much of every list as fits.  Rank 0 packs straight into its receive slot.
+    uint64_t *dst_off = c->rank == 0 ? c->recv_off : c->pack_off;
+    uint32_t *dst_val = c->rank == 0 ? c->recv_val : c->pack_val;
+    uint64_t hdr[HDR];
     uint64_t at = nlists, used = 0;
     std::vector<uint64_t> fit(nlists);
     for (int k = 0; k < nlists; k++) {
         hdr[k] = v[k].count;
         fit[k] = std::min<uint64_t>(v[k].count, room - used);
         if (fit[k]) {
-            CUC(cudaMemcpyAsync(c->pack_off + at, v[k].d_off, fit[k] * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
-            CUC(cudaMemcpyAsync(c->pack_val + at, v[k].d_val, fit[k] * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+            CUC(cudaMemcpyAsync(dst_off + at, v[k].d_off, fit[k] * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+            CUC(cudaMemcpyAsync(dst_val + at, v[k].d_val, fit[k] * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
         }
         at += fit[k]; used += fit[k];
     }
     // pageable source: the runtime stages it before returning, so `hdr` may go out of scope
-    CUC(cudaMemcpyAsync(c->pack_off, hdr, (size_t)nlists * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    CUC(cudaMemcpyAsync(dst_off, hdr, (size_t)nlists * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
 
     // one grouped NCCL operation moves every rank's packed buffers to rank 0
     NC(nccl().GroupStart());
@@ -242,40 +226,100 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
     NC(nccl().GroupEnd());
 
     if (c->rank != 0) {
-        // what did not fit travels point-to-point; rank 0 posts the matching receives when it completes the gather.
-        // Stream order keeps the lists alive: their cudaFreeAsync is queued behind these sends.
-        for (int k = 0; k < nlists; k++) {
-            if (fit[k] < v[k].count) {
-                NC(nccl().Send(v[k].d_off + fit[k], v[k].count - fit[k], ncclUint64, 0, c->comm, stream));
-                NC(nccl().Send(v[k].d_val + fit[k], v[k].count - fit[k], ncclUint32, 0, c->comm, stream));
+        // what did not fit travels point-to-point; rank 0 posts the matching receives before ITS call returns
+        bool any = false;
+        for (int k = 0; k < nlists; k++) any = any || fit[k] < v[k].count;
+        if (any) {
+            NC(nccl().GroupStart());
+            for (int k = 0; k < nlists; k++) {
+                if (fit[k] < v[k].count) {
+                    NC(nccl().Send(v[k].d_off + fit[k], v[k].count - fit[k], ncclUint64, 0, c->comm, stream));
+                    NC(nccl().Send(v[k].d_val + fit[k], v[k].count - fit[k], ncclUint32, 0, c->comm, stream));
+                }
             }
+            NC(nccl().GroupEnd());
         }
+        CUC(cudaEventRecord(c->t1, stream));
+        c->timed = true;
+        // the copies and sends above read the lists on THIS stream: release them in this stream's order
+        for (int k = 0; k < nlists; k++) mmg_internal_results_free_on(lists[k], stream);
         return MMG_OK;
     }
 
-    // rank 0: own buffers + everybody's headers (read back asynchronously)
-    CUC(cudaMemcpyAsync(c->recv_off, c->pack_off, c->cap * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
-    CUC(cudaMemcpyAsync(c->recv_val, c->pack_val, c->cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-    CUC(cudaMemcpy2DAsync(c->hdr_host, 64 * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t),
+    // ---- rank 0: everybody's headers, then the receives of what did not fit
+    CUC(cudaMemcpy2DAsync(c->hdr_host, HDR * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t),
                           (size_t)nlists * sizeof(uint64_t), c->world, cudaMemcpyDeviceToHost, stream));
+    CUC(cudaEventRecord(c->hdr_ready, stream));
+    CUC(cudaEventSynchronize(c->hdr_ready));
     mmg_gathered *g = new mmg_gathered();
     g->nlists = nlists;
     g->counts.assign(nlists, 0);
     g->pieces.resize(nlists);
-    g->pending = true;
-    g->comm = c;
     g->stream = stream;
-    g->own = v;
-    CUC(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
-    CUC(cudaEventRecord(g->ready, stream));
-    c->inflight = g;
+    auto bail = [&](int code) { mmg_gathered_free(g); return code; };
+    const uint64_t *all = c->hdr_host;
+    struct Spill { int rank; uint64_t *off; uint32_t *val; uint64_t n; };
+    std::vector<Spill> spills;
+    for (int r = 0; r < c->world; r++) {
+        uint64_t pos = nlists, used_r = 0;
+        for (int k = 0; k < nlists; k++) {
+            const uint64_t n = all[(size_t)r * HDR + k];
+            const uint64_t f = std::min<uint64_t>(n, room - used_r);
+            g->counts[k] += n;
+            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
+            pos += f; used_r += f;
+            if (f < n) {
+                const uint64_t rest = n - f;
+                uint64_t *so = nullptr; uint32_t *sv = nullptr;
+                if (cudaMallocAsync((void **)&so, rest * sizeof(uint64_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
+                g->owned.push_back(so);
+                if (cudaMallocAsync((void **)&sv, rest * sizeof(uint32_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
+                g->owned.push_back(sv);
+                if (r == 0) {
+                    if (cudaMemcpyAsync(so, v[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+                        cudaMemcpyAsync(sv, v[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                        return bail(err(MMG_ERR_CUDA, "copying rank 0's overflow failed"));
+                } else {
+                    spills.push_back({r, so, sv, rest});
+                }
+                g->pieces[k].push_back({so, sv, rest});
+            }
+        }
+    }
+    if (!spills.empty()) {
+        // same order per peer as the sends (list by list, offsets then values); one group so that all peers stream at once
+        if (nccl().GroupStart() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupStart failed"));
+        for (const Spill &s : spills) {
+            if (nccl().Recv(s.off, s.n, ncclUint64, s.rank, c->comm, stream) != ncclSuccess ||
+                nccl().Recv(s.val, s.n, ncclUint32, s.rank, c->comm, stream) != ncclSuccess)
+                return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
+        }
+        if (nccl().GroupEnd() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupEnd failed"));
+    }
+    if (cudaEventRecord(c->t1, stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
+    c->timed = true;
+    if (cudaEventCreateWithFlags(&g->landed, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventRecord(g->landed, stream) != cudaSuccess)
+        return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
+    for (int k = 0; k < nlists; k++) mmg_internal_results_free_on(lists[k], stream);
     *out = g;
+    return MMG_OK;
+}
+
+// Blocks until everything this rank enqueued for its gathers has executed (sends delivered / lists landed).
+// *ms_last (may be NULL) receives the device time of the last gather on this rank's gather stream.
+int mmg_comm_wait(mmg_comm *c, float *ms_last) {
+    if (!c) return err(MMG_ERR_ARG, "null communicator");
+    CUC(cudaStreamSynchronize(c->stream));
+    if (ms_last) {
+        *ms_last = 0.f;
+        if (c->timed && cudaEventElapsedTime(ms_last, c->t0, c->t1) != cudaSuccess) { cudaGetLastError(); *ms_last = 0.f; }
+    }
     return MMG_OK;
 }
 
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list) {
     if (!g || list < 0 || list >= g->nlists) return 0;
-    finish_gather(const_cast<mmg_gathered *>(g));
     return g->counts[list];
 }
 
@@ -283,7 +327,7 @@ uint64_t mmg_gathered_count(const mmg_gathered *g, int list) {
 // Valid until the next mmg_comm_gather on the same communicator.
 int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32_t *values) {
     if (!g || list < 0 || list >= g->nlists) return err(MMG_ERR_ARG, "bad gathered list");
-    if (int rc = finish_gather(const_cast<mmg_gathered *>(g)); rc != MMG_OK) return rc;
+    if (int rc = wait_landed(const_cast<mmg_gathered *>(g)); rc != MMG_OK) return rc;
     uint64_t at = 0;
     for (const auto &p : g->pieces[list]) {
         if (offsets) CUC(cudaMemcpy(offsets + at, p.off, p.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -297,11 +341,23 @@ int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32
     return MMG_OK;
 }
 
+// Device-resident pieces of list `list` in file order (rank 0): up to `cap` (pointer, pointer, n) triples;
+// returns the number of pieces.  Valid until the next mmg_comm_gather on the same communicator.
+int mmg_gathered_pieces(const mmg_gathered *g, int list, const uint64_t **offs, const uint32_t **vals, uint64_t *ns, int cap) {
+    if (!g || list < 0 || list >= g->nlists) return 0;
+    if (wait_landed(const_cast<mmg_gathered *>(g)) != MMG_OK) return 0;
+    int n = 0;
+    for (const auto &p : g->pieces[list]) {
+        if (n < cap) { if (offs) offs[n] = p.off; if (vals) vals[n] = p.val; if (ns) ns[n] = p.n; }
+        n++;
+    }
+    return n;
+}
+
 void mmg_gathered_free(mmg_gathered *g) {
     if (!g) return;
-    finish_gather(g);
-    if (g->ready) cudaEventDestroy(g->ready);
-    for (void *p : g->owned) cudaFree(p);
+    for (void *p : g->owned) cudaFreeAsync(p, g->stream);     // behind the receives that fill them
+    if (g->landed) cudaEventDestroy(g->landed);
     delete g;
 }
 

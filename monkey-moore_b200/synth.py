@@ -30,6 +30,16 @@ def synth_bytes(nbytes, seed, first_byte=0, byte_mask=0xFF):
     return np.ascontiguousarray(b)
 
 
+def mt19937_bytes(nbytes, seed=42):
+    """The reference benchmark's data (benchmarks/bench_search.cpp:11-22 of the reference): ``std::mt19937 rng(seed)``
+    drawn through ``std::uniform_int_distribution<unsigned>(0, 255)``.  libstdc++ (GCC >= 11) maps a 32-bit engine
+    onto a power-of-two range with Lemire's multiply-shift, which for 256 values is the TOP byte of every 32-bit
+    draw and never rejects; numpy's legacy seeding is init_genrand(seed), i.e. the same engine state."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(int(seed))
+    return np.ascontiguousarray((bg.random_raw(int(nbytes)) >> np.uint64(24)).astype(np.uint8))
+
+
 def synth_fill_device(tensor, seed, first_byte=0, byte_mask=0xFF):
     """Fills a CUDA uint8 torch tensor (size and first_byte multiples of 8) with stream bytes."""
     from . import _check, lib

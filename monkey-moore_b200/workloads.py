@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .synth import synth_bytes
+from .synth import mt19937_bytes, synth_bytes
 
 MiB = 1 << 20
 GiB = 1 << 30
@@ -38,6 +38,9 @@ class Workload:
     n_planted: int = 0
     block_size: int = 524288       # SearchConfig default (include/mmoore/search_engine.hpp:36)
     plant_pattern: Optional[dict] = None
+    generator: str = "splitmix"    # "splitmix": counter based (synth.py);  "mt19937": the reference benchmark's generator
+    scaling: str = "weak"          # "weak": `size` bytes per GPU;  "strong": `size` bytes in total, split over the GPUs
+    single_gpu_size: int = 0       # bytes scanned when a multi-GPU configuration is measured on ONE GPU (its per-GPU slice)
 
     def scaled(self, size):
         return dataclasses.replace(self, size=int(size))
@@ -45,8 +48,10 @@ class Workload:
 
 WORKLOADS = {
     # configs[0]: the reference's own bench_search case (benchmarks/bench_search.cpp), 6-char keyword
-    "cfg1": Workload("cfg1", "8-bit relative search, 6-char ASCII keyword 'monkey', 16 MiB", 8, 16 * MiB, 0x5EED0001,
-                     [Search("8bit-monkey", dict(keyword="monkey", wildcard=0))], n_planted=64),
+    # data: std::mt19937(42) + uniform_int_distribution<unsigned>(0, 255), exactly benchmarks/bench_search.cpp:11-22
+    "cfg1": Workload("cfg1", "8-bit relative search, 6-char ASCII keyword 'monkey', 16 MiB (mt19937(42) data of the reference benchmark)",
+                     8, 16 * MiB, 0x5EED0001, [Search("8bit-monkey", dict(keyword="monkey", wildcard=0))], n_planted=64,
+                     generator="mt19937"),
     # configs[1]: the configuration the metric is quoted on
     "cfg2": Workload("cfg2", "16-bit LE+BE relative search, 8-char keyword 'mo*key*s' (2 wildcards), 512 MiB", 16,
                      512 * MiB, 0x5EED0002,
@@ -58,7 +63,8 @@ WORKLOADS = {
     # configs[3]
     "cfg4": Workload("cfg4", "16-bit LE custom character sequence (49-char Hiragana table), 6-char keyword, 16 GiB",
                      16, 16 * GiB, 0x5EED0004,
-                     [Search("16le-kana", dict(keyword="わたしたちは", wildcard=0, char_seq=HIRAGANA))], n_planted=4096),
+                     [Search("16le-kana", dict(keyword="わたしたちは", wildcard=0, char_seq=HIRAGANA))], n_planted=4096,
+                     scaling="strong", single_gpu_size=2 * GiB),
     # configs[4]
     "cfg5": Workload("cfg5", "8-bit 3-char keyword 'abc' over a 16-symbol low-entropy blob, 64 GiB (8 x 8 GiB)", 8,
                      8 * GiB, 0x5EED0005, [Search("8bit-abc-dense", dict(keyword="abc", wildcard=0))], byte_mask=0x0F),
@@ -76,7 +82,18 @@ def _pattern_values(pat) -> List[Optional[int]]:
     return [None if c == wc else (idx.get(c, 0) if seq else c) for c in cps]
 
 
+_PATCH_CACHE = {}
+
+
 def planted_patches(w: Workload, total_size: int) -> List[Tuple[int, bytes]]:
+    """Cached front of :func:`_planted_patches` (the list depends only on the workload's constants and the file size)."""
+    key = (w.key, w.size, w.seed, w.n_planted, w.block_size, w.bits, total_size)
+    if key not in _PATCH_CACHE:
+        _PATCH_CACHE[key] = _planted_patches(w, total_size)
+    return _PATCH_CACHE[key]
+
+
+def _planted_patches(w: Workload, total_size: int) -> List[Tuple[int, bytes]]:
     """Deterministic (file offset, bytes) patches that plant shifted copies of the workload's pattern.
     Half of the 16-bit plants sit at odd byte offsets; big-endian searches get big-endian plants; some
     plants sit right before a block edge so the overlap logic is exercised."""
@@ -119,7 +136,12 @@ def host_blob(w: Workload, first_byte=0, nbytes=None, total_size=None) -> np.nda
     """The bytes [first_byte, first_byte + nbytes) of the workload's file, on the host."""
     total_size = total_size or w.size
     nbytes = total_size - first_byte if nbytes is None else nbytes
-    b = synth_bytes(nbytes, w.seed, first_byte=first_byte, byte_mask=w.byte_mask)
+    if w.generator == "mt19937":
+        b = mt19937_bytes(first_byte + nbytes, 42)[first_byte:]
+        if w.byte_mask != 0xFF:
+            b = b & np.uint8(w.byte_mask)
+    else:
+        b = synth_bytes(nbytes, w.seed, first_byte=first_byte, byte_mask=w.byte_mask)
     for off, raw in planted_patches(w, total_size):
         lo, hi = max(off, first_byte), min(off + len(raw), first_byte + nbytes)
         if lo < hi:
@@ -134,6 +156,11 @@ def device_blob(w: Workload, first_byte=0, nbytes=None, total_size=None, device=
     from .synth import synth_fill_device
     total_size = total_size or w.size
     nbytes = total_size - first_byte if nbytes is None else nbytes
+    if w.generator != "splitmix":          # small host-generated blobs (cfg1: 16 MiB) are simply uploaded
+        host = host_blob(w, first_byte, nbytes, total_size)
+        buf = torch.empty(nbytes + 64, dtype=torch.uint8, device=device)
+        buf[:nbytes] = torch.from_numpy(host).to(device)
+        return buf[:nbytes]
     lo8 = first_byte & ~7
     hi8 = (first_byte + nbytes + 7) & ~7
     buf = torch.empty(hi8 - lo8 + 64, dtype=torch.uint8, device=device)   # 64 spare bytes keep 16-byte reads in bounds

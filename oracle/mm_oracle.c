@@ -293,6 +293,7 @@ mmo_pattern *mmo_compile_values(const int16_t *values, int n, int bits, int *err
 
 int mmo_keyword_len(const mmo_pattern *p) { return p->L; }
 int mmo_mode(const mmo_pattern *p) { return p->mode; }
+int mmo_elem_bits(const mmo_pattern *p) { return p->bits; }
 
 static inline uint32_t load_elem(const mmo_pattern *p, const uint8_t *base, uint64_t i) {
     if (p->bits == 8) return base[i];

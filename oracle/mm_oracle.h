@@ -45,6 +45,7 @@ mmo_pattern *mmo_compile_values(const int16_t *values, int n, int bits, int *err
 void mmo_free(mmo_pattern *p);
 
 int mmo_keyword_len(const mmo_pattern *p);
+int mmo_elem_bits(const mmo_pattern *p);      /* 8 or 16 */
 /* 0 = simple_relative, 1 = wildcard_relative, 2 = value_scan */
 int mmo_mode(const mmo_pattern *p);
 
@@ -84,6 +85,17 @@ int64_t mmo_engine(const mmo_pattern *p, const uint8_t *file, uint64_t size,
 
 /* Number of blocks compute_search_blocks() yields (progress-callback count). */
 uint64_t mmo_num_blocks(uint64_t size, uint32_t block_size);
+
+/* mm_oracle_stream.c: the engine (64-bit offsets) over blocks [first_block, first_block + nblocks) of a SYNTHETIC
+ * file that is regenerated block by block (counter-based generator of monkey-moore_b200/synth.py + planted
+ * patches, ascending by offset), folded into an order-sensitive digest out3 = {count, S0, S1}; optionally the
+ * ordered list itself (out_off / out_vals, up to list_cap matches).  nthreads host threads work on disjoint blocks. */
+uint64_t mmo_digest_mix(uint64_t off, uint32_t v0, uint32_t v1);
+int64_t mmo_engine_synth(const mmo_pattern *p, uint64_t seed, uint32_t byte_mask, uint64_t total_size,
+                         uint32_t block_size, uint64_t first_block, uint64_t nblocks, int big_endian,
+                         const uint64_t *patch_off, const uint32_t *patch_len, const uint8_t *patch_bytes,
+                         uint64_t npatches, int nthreads, uint64_t *out3,
+                         uint64_t *out_off, uint32_t *out_vals, uint64_t list_cap);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,10 @@ class Oracle:
                                        u64p, u32p, C.c_uint64]
             lib.mmo_num_blocks.restype = C.c_uint64
             lib.mmo_num_blocks.argtypes = [C.c_uint64, C.c_uint32]
+            lib.mmo_engine_synth.restype = C.c_int64
+            lib.mmo_engine_synth.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64,
+                                             C.c_uint64, C.c_int, u64p, u32p, C.c_void_p, C.c_uint64, C.c_int, u64p,
+                                             u64p, u32p, C.c_uint64]
             cls._lib = lib
         return cls._lib
 
@@ -129,6 +133,75 @@ class Oracle:
         self.lib().mmo_engine(self.h, fb.ctypes.data, fb.size, block_size, int(big_endian), int(wrap32),
                               off.ctypes.data_as(u64p), vals.ctypes.data_as(u32p), n)
         return off[:n], vals[:n]
+
+
+    def engine_synth(self, seed, byte_mask, total_size, block_size, first_block=0, nblocks=0, big_endian=False,
+                     patches=(), threads=1, want_list=False, list_cap=1 << 24):
+        """The engine (64-bit offsets) over blocks of a SYNTHETIC file regenerated block by block on the host
+        (oracle/mm_oracle_stream.c).  patches: [(offset, bytes)] in application order.
+        -> dict(count, s0, s1[, offsets, values])   (s0/s1: order-sensitive digest, see :func:`digest`)"""
+        order = sorted(range(len(patches)), key=lambda k: patches[k][0])      # stable: equal offsets keep their order
+        po = np.array([patches[k][0] for k in order], dtype=np.uint64)
+        pl = np.array([len(patches[k][1]) for k in order], dtype=np.uint32)
+        pb = np.frombuffer(b"".join(patches[k][1] for k in order) or b"\0", dtype=np.uint8).copy()
+        out3 = np.zeros(3, np.uint64)
+        off = vals = None
+        if want_list:
+            off = np.zeros(list_cap, np.uint64)
+            vals = np.zeros((list_cap, 2), np.uint32)
+        n = self.lib().mmo_engine_synth(self.h, int(seed) & ((1 << 64) - 1), int(byte_mask), int(total_size),
+                                        int(block_size), int(first_block), int(nblocks), int(bool(big_endian)),
+                                        po.ctypes.data_as(u64p), pl.ctypes.data_as(u32p), pb.ctypes.data, len(order),
+                                        int(threads), out3.ctypes.data_as(u64p),
+                                        off.ctypes.data_as(u64p) if want_list else None,
+                                        vals.ctypes.data_as(u32p) if want_list else None, list_cap if want_list else 0)
+        if n < 0:
+            raise MMError("mmo_engine_synth: bad arguments")
+        r = dict(count=int(out3[0]), s0=int(out3[1]), s1=int(out3[2]))
+        if want_list:
+            k = min(n, list_cap)
+            r["offsets"], r["values"] = off[:k], vals[:k]
+        return r
+
+
+_M64 = (1 << 64) - 1
+
+
+def digest(offsets, values, first_index=0):
+    """Order-sensitive digest of a match list, the numpy twin of oracle/mm_oracle_stream.c:
+    h_i = mix64(off_i + G * ((v0 | v1 << 16) + 1));  -> (count, S0 = sum h_i, S1 = sum h_i * (2 (first_index + i) + 1))."""
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(off)
+    if n == 0:
+        return 0, 0, 0
+    v = np.asarray(values)
+    if v.ndim == 2:
+        word = (v[:, 0].astype(np.uint64) & np.uint64(0xFFFF)) | (v[:, 1].astype(np.uint64) << np.uint64(16))
+    else:
+        word = v.astype(np.uint64)
+    s0 = s1 = 0
+    with np.errstate(over="ignore"):
+        for a in range(0, n, 1 << 22):          # bounded temporaries for 10^8-entry lists
+            b = min(n, a + (1 << 22))
+            x = off[a:b] + np.uint64(0x9E3779B97F4A7C15) * (word[a:b] + np.uint64(1))
+            z = x + np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            h = z ^ (z >> np.uint64(31))
+            idx = np.arange(first_index + a, first_index + b, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+            s0 = (s0 + int(h.sum(dtype=np.uint64))) & _M64
+            s1 = (s1 + int((h * idx).sum(dtype=np.uint64))) & _M64
+    return n, s0, s1
+
+
+def compose(parts):
+    """(count, S0, S1) of the concatenation of adjacent ranges, each digested with first_index = 0."""
+    n = s0 = s1 = 0
+    for c, a, b in parts:
+        s1 = (s1 + b + 2 * n * a) & _M64
+        s0 = (s0 + a) & _M64
+        n += c
+    return n, s0, s1
 
 
 class Ref:
@@ -222,20 +295,26 @@ class Ref:
 
     @classmethod
     def engine(cls, bits, path, keyword=None, wildcard=ord("*"), char_seq=(), values=None, big_endian=False,
-               threads=1, block=524288, preview_width=50, previews=False, abort_after=0):
-        """-> dict(offsets, maps, previews, progress=[(pct, step)])"""
+               threads=1, block=524288, preview_width=50, previews=False, abort_after=0, count_only=False):
+        """-> dict(offsets, maps, previews, progress=[(pct, step)]); count_only=True -> dict(count, seconds) where
+        seconds covers SearchEngine::run alone (not the conversion of its result maps to Python objects)."""
         lib = cls.lib()
         keep, args = cls._pattern_args(bits, keyword, wildcard, char_seq, values)
         bits_, kwp, L, wc, sqp, nseq, vp, nv = args
         if vp is None:
             dummy = np.zeros(1, np.int16)
             vp = dummy.ctypes.data_as(i16p)
+        import time as _time
+        t0 = _time.perf_counter()
         h = lib.ref_engine_run(bits_, os.fsencode(path), 0 if values is not None else 1, int(big_endian), kwp, L,
                                wc, sqp, nseq, vp, nv, threads, block, preview_width, int(previews), abort_after)
+        seconds = _time.perf_counter() - t0
         if not h:
             raise MMError(lib.ref_last_error().decode())
         try:
             n = lib.ref_engine_count(h)
+            if count_only:
+                return dict(count=int(n), seconds=seconds)
             ne = lib.ref_engine_entries(h)
             npg = lib.ref_engine_progress_count(h)
             off = np.zeros(max(n, 1), np.uint64)

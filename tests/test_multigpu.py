@@ -1,6 +1,9 @@
 """Multi-GPU (needs >= 2 devices; skipped otherwise): every rank scans its block range on its own GPU,
 the library gathers the match lists to rank 0 over NCCL, and the result equals the one-GPU scan and the
-oracle -- both for a sparse workload and for a dense one that overflows the packed buffer (spill path)."""
+oracle -- for a sparse workload, for a dense one that overflows the packed buffer (spill path), and for a
+dense one with more than 10^7 matches whose lists are released right after the gather call (the library
+must keep them alive behind its own sends) while a collective of ANOTHER communicator follows at once."""
+import dataclasses
 import os
 import socket
 import sys
@@ -24,6 +27,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import monkey_moore_b200 as mm
     import monkey_moore_b200.workloads as wl
+    from _oracle import Oracle, compose, digest
     from monkey_moore_b200.distributed import shard_bytes
 
     def bcast(raw):
@@ -31,8 +35,14 @@ def _worker(rank, world, port, q):
         dist.broadcast(t, src=0)
         return bytes(t.cpu().tolist())
 
+    def oracle_of(w, s):
+        pat = s.pattern
+        return Oracle(w.bits, keyword=pat.get("keyword"), wildcard=pat.get("wildcard", 0),
+                      char_seq=pat.get("char_seq", ()), values=pat.get("values"))
+
     comm = mm.Comm(rank, world, bcast, capacity=256)
     ok = {}
+    # ---- small cases: full lists against the in-memory oracle and the one-GPU scan
     for key, size in (("cfg2", 24 << 20), ("cfg5", 6 << 20)):
         w = wl.WORKLOADS[key].scaled(size)
         progs = [mm.Program(w.bits, **s.pattern) for s in w.searches]
@@ -43,17 +53,45 @@ def _worker(rank, world, port, q):
                 for p, s in zip(progs, w.searches)]
         got = comm.gather(held, fetch=True)
         if rank == 0:
-            from _oracle import Oracle
             whole = wl.host_blob(w)
             for p, s, (off, val) in zip(progs, w.searches, got):
-                pat = s.pattern
-                o = Oracle(w.bits, keyword=pat.get("keyword"), wildcard=pat.get("wildcard", 0),
-                           char_seq=pat.get("char_seq", ()), values=pat.get("values"))
-                exp, expv = o.engine(whole, w.block_size, big_endian=s.big_endian, wrap32=False)
+                exp, expv = oracle_of(w, s).engine(whole, w.block_size, big_endian=s.big_endian, wrap32=False)
                 one = p.engine_scan(whole, w.block_size, big_endian=s.big_endian)
                 o1, v1 = one.arrays()
                 ok[key + ":" + s.name] = (off.tolist() == exp.tolist() and val.tolist() == expv.tolist()
                                           and o1.tolist() == exp.tolist(), len(exp))
+
+    # ---- dense case, > 10^7 matches: 4-symbol alphabet, lists freed immediately, two gathers back to back, then a
+    # collective of torch's communicator while this rank's spill sends may still be in flight
+    w = dataclasses.replace(wl.WORKLOADS["cfg5"], size=768 << 20, byte_mask=0x03)
+    s = w.searches[0]
+    prog = mm.Program(w.bits, **s.pattern)
+    overlap = (prog.keyword_len - 1) * (w.bits // 8)
+    b0, nb, lo, hi = shard_bytes(w.size, w.block_size, overlap, rank, world)
+    blob = wl.device_blob(w, first_byte=lo, nbytes=hi - lo, total_size=w.size)
+    gathered = []
+    for _ in range(2):
+        res = prog.engine_scan(blob, w.block_size, file_size=w.size, first_block=b0, num_blocks=nb)
+        g = comm.gather([res], lazy=True)
+        res.close()                                      # released while the gather may still read it
+        scratch = torch.full((64 << 20,), 0xFF, dtype=torch.uint8, device="cuda")     # recycle freed memory eagerly
+        del scratch
+        gathered.append(g)
+    flag = torch.ones(1, device="cuda")
+    dist.all_reduce(flag)                                # another communicator's collective right behind the gathers
+    o = oracle_of(w, s)
+    r = o.engine_synth(w.seed, w.byte_mask, w.size, w.block_size, b0, nb, False, [], threads=max(1, (os.cpu_count() or 2) // world))
+    t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in (r["count"], r["s0"], r["s1"])], dtype=torch.int64, device="cuda")
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    if rank == 0:
+        want = compose([tuple(int(x) & ((1 << 64) - 1) for x in p.tolist()) for p in parts])
+        off, val = gathered[1].fetch()[0]
+        good = digest(off, val) == want and bool(np.all(off[1:] > off[:-1])) and gathered[0].counts()[0] == want[0]
+        ok["dense4:" + s.name] = (good, int(want[0]))
+        for g in gathered:
+            g.close()
+    comm.wait()
     if rank == 0:
         q.put(ok)
     dist.barrier()
@@ -73,9 +111,10 @@ def test_sharded_scan_and_nccl_gather():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = q.get(timeout=300)
+    res = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res and all(good for good, _ in res.values()), res
     assert res["cfg5:8bit-abc-dense"][1] > 1000      # dense enough to exercise the spill path
+    assert res["dense4:8bit-abc-dense"][1] > 10_000_000
