@@ -74,6 +74,9 @@ struct DeviceInfo {
     int device = -1;
     int sms = 0;
     cudaStream_t own_stream = nullptr;   // this library's non-blocking stream (callers without mmg_set_stream)
+    cudaStream_t gather_stream = nullptr; // comm.cu: copies and NCCL calls of the result gathers (lives as long as the process:
+                                          // result lists that a gather read are released in this stream's order, possibly
+                                          // long after the communicator itself is gone)
     Lane lanes[2];
     unsigned next_lane = 0;
     std::mutex mu;
@@ -93,6 +96,7 @@ DeviceInfo &device_info() {
     try {
         CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
         CU(cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d.gather_stream, cudaStreamNonBlocking));
         for (Lane &l : d.lanes) {
             CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
@@ -145,6 +149,7 @@ struct TiledState {
     MmgGeom G{};
     MmgScratch X{};
     int lag_bytes = 0, grid = 0;
+    bool sparse = false;          // resolved by k_resolve_sparse (one warp per block): no per-sub-tile match bookkeeping exists
     uint64_t total_warps = 0, per_warp = 0, cap = 0;
     uint64_t generation = 0;      // workspace generation of this scan's last enqueue
     Workspace *ws = nullptr;
@@ -280,7 +285,7 @@ void enqueue_tiled(mmg_results *res) {
     auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
     // zero state
     const size_t o_status = carve(4 * sizeof(uint64_t));
-    const size_t o_ticket = carve(2 * sizeof(uint32_t));
+    const size_t o_ticket = carve(4 * sizeof(uint32_t));
     const size_t o_lookback = carve((size_t)G.nseg * sizeof(uint64_t));
     const size_t zero_need = off;
     off = 0;
@@ -318,7 +323,17 @@ void enqueue_tiled(mmg_results *res) {
     if (res->launches == 0) CU(cudaEventRecord(res->ev[1], stream));      // ev[1] -> ev[2] brackets the filter kernel alone
     CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
     if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
-    CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
+    // A pattern whose previous scan left only a few events per engine block is resolved by the warp-per-block kernel;
+    // should this scan turn out denser the kernel says so and finish_tiled() runs the general one over the same events.
+    {
+        const mmg_program *prog = res->rq.prog;
+        const uint64_t hint_bytes = prog->last_bytes.load(), hint_events = prog->last_events.load();
+        static const bool no_sparse = getenv("MMG_NO_SPARSE_RESOLVE") != nullptr;
+        t.sparse = !no_sparse && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
+                   (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
+    }
+    if (t.sparse) CU(mmg_launch_resolve_sparse(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
+    else CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
     ws.dirty = false;
     res->launches += t.G.segs_per_block > 1 ? 4 : 2;
     t.generation = ++ws.generation;
@@ -398,10 +413,28 @@ void finish_tiled(mmg_results *res) {
         }
         CU(cudaStreamSynchronize(stream));
     }
-    res->rq.prog->last_events_per_warp = status[0];
-    res->rq.prog->last_events = status[1];
+    const uint64_t ev_max = status[0], ev_total = status[1];
+    if (t.sparse && status[4] != 0) {
+        // a block held more events than the sparse kernel stages: the general resolve kernel over the same event lists
+        // (the zero state was restored, the lists are intact unless another scan used the workspace since)
+        std::lock_guard<std::mutex> lock(res->dev->mu);
+        t.sparse = false;
+        if (t.generation == t.ws->generation) {
+            CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
+            res->launches += t.G.segs_per_block > 1 ? 3 : 1;
+        } else {
+            res->rq.prog->last_events = ev_total;       // so that the re-run picks the general kernel
+            res->rq.prog->last_bytes = res->rq.S;
+            enqueue_tiled(res);
+        }
+        CU(cudaEventRecord(res->ev[3], stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    res->rq.prog->last_events_per_warp = ev_max;
+    res->rq.prog->last_events = ev_total;
+    res->rq.prog->last_bytes = res->rq.S;
     res->rq.prog->last_count = status[2];
-    res->stats.events = status[1];
+    res->stats.events = ev_total;
     res->count = status[2];
     if (res->count > t.cap) {
         // the optimistic buffer was too small: allocate exactly and emit again from the stored bases -- or, when
@@ -411,7 +444,7 @@ void finish_tiled(mmg_results *res) {
             free_results(res);
             t.cap = res->count;
             alloc_results(res, t.cap);
-            if (t.generation == t.ws->generation) {
+            if (t.generation == t.ws->generation && !t.sparse) {
                 CU(mmg_launch_emit(P, t.G, t.X, res->d_off, res->d_val, stream));
                 res->launches += 1;
             } else {
@@ -750,6 +783,9 @@ int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out) {
     out->d_off = r ? r->d_off : nullptr;
     out->d_val = r ? r->d_val : nullptr;
     return MMG_OK;
+}
+void *mmg_internal_gather_stream(void) {
+    try { return device_info().gather_stream; } catch (const ScanError &) { return nullptr; }
 }
 void mmg_internal_results_free_on(const mmg_results *r, void *stream) {
     if (r) const_cast<mmg_results *>(r)->free_stream = static_cast<cudaStream_t>(stream);

@@ -15,7 +15,7 @@
 //      matching receives before it returns -- a pending send never outlives the call that caused it,
 //      so no later collective (of this or any other communicator) can queue behind an unmatched send.
 //
-// Everything runs on the communicator's OWN stream: the scan streams never wait for NCCL, and a
+// Everything runs on a dedicated, process-wide gather stream of the device: the scan streams never wait for NCCL, and a
 // list that is still being read by a send is released in gather-stream order (the results object is
 // told to free itself on this stream), so the stream-ordered allocator cannot recycle it early.
 // NCCL is loaded with dlopen so that single-GPU users (the GUI drop-in) need no NCCL installation.
@@ -34,6 +34,7 @@
 struct mmg_results_view { uint64_t count; const uint64_t *d_off; const uint32_t *d_val; };
 extern "C" int mmg_internal_results_view(const mmg_results *r, mmg_results_view *out);
 extern "C" void mmg_internal_results_free_on(const mmg_results *r, void *stream);
+extern "C" void *mmg_internal_gather_stream(void);
 extern "C" void mmg_internal_set_error(const char *msg);
 
 namespace {
@@ -93,7 +94,7 @@ struct mmg_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     uint64_t cap = 0;               // entries per packed buffer (header included)
-    cudaStream_t stream = nullptr;  // every copy and NCCL call of the gather runs here
+    cudaStream_t stream = nullptr;  // every copy and NCCL call of the gather runs here (the device's process-wide gather stream)
     cudaEvent_t t0 = nullptr, t1 = nullptr, hdr_ready = nullptr;   // device time of the last gather; headers landed
     bool timed = false;
     uint64_t *pack_off = nullptr;
@@ -126,8 +127,7 @@ void destroy_comm(mmg_comm *c) {
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->hdr_ready) cudaEventDestroy(c->hdr_ready);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+    delete c;       // the stream belongs to the device state: lists released after this point still name it
 }
 
 int wait_landed(mmg_gathered *g) {
@@ -160,7 +160,8 @@ int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, m
     std::memcpy(&id, id128, sizeof(id));
     auto build = [&]() -> int {
         NC(nccl().CommInitRank(&c->comm, world, id, rank));
-        CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->stream = static_cast<cudaStream_t>(mmg_internal_gather_stream());
+        if (!c->stream) return err(MMG_ERR_CUDA, "no usable CUDA device");
         CUC(cudaEventCreate(&c->t0));
         CUC(cudaEventCreate(&c->t1));
         CUC(cudaEventCreateWithFlags(&c->hdr_ready, cudaEventDisableTiming));

@@ -217,8 +217,14 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
             // depth-2 refinement: comparisons 0 and 1 look at adjacent element pairs with exact arithmetic
             d.d2ok = (!d.modular && d.ncheck >= 2 && d.chk[0].lag == 1 && d.chk[1].lag == 1 &&
                       d.chk[1].i == d.chk[0].i - 1 && pass_first) ? 1 : 0;
-            for (size_t j = 0; j < keys.size(); j++)
-                d.keys[j] = ((0x10000u - 256u - static_cast<uint32_t>(keys[j])) & 0xFFFFu) * 0x00010001u;
+            for (size_t j = 0; j < keys.size(); j++) {
+                const uint32_t k = static_cast<uint32_t>(keys[j]);
+                // difference registers with a biased current pair hold 256 + d in both halves ...
+                d.keys[j] = ((0x10000u - 256u - k) & 0xFFFFu) * 0x00010001u;
+                // ... those with a biased PREVIOUS pair (odd lags, scan_kernels.cu filter8) hold d - 256 in the low half
+                // and d - 257 in the high half (the low half always borrows)
+                d.pkeys[j] = (((257u - k) & 0xFFFFu) << 16) | ((256u - k) & 0xFFFFu);
+            }
         } else {
             std::vector<uint32_t> keys;
             auto add_key = [&](int32_t diff) {

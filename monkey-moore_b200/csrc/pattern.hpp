@@ -28,6 +28,7 @@ struct mmg_program {
     mutable std::atomic<uint64_t> last_count{0};
     mutable std::atomic<uint64_t> last_events_per_warp{0};
     mutable std::atomic<uint64_t> last_events{0};          // total events of the previous scan
+    mutable std::atomic<uint64_t> last_bytes{0};           // bytes the previous scan covered (0: no scan yet)
 
     int value_of(uint32_t c) const;        // code point, or index in char_seq (0 when absent)
 };

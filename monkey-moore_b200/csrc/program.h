@@ -45,7 +45,8 @@ struct MmgProgram {
     // Differences (mod 2^(8W)) of comparison 0 that do NOT lead to a J0 advance, stored as the
     // SWAR constant the filter kernel consumes:  W=1: k * 0x01010101 ;  W=2: ((1-k) & 0xFFFF) * 0x00010001
     uint32_t keys[MMG_MAXL + 1];
-    // 16-bit pre-filter constants: upper half (1 - k), lower half (-k)  (scan_kernels.cu prefilter16)
+    // 16-bit pre-filter constants: upper half (1 - k), lower half (-k)  (scan_kernels.cu prefilter16);
+    // 8-bit, odd lags: the key constants of the difference registers whose PREVIOUS pair carries the bias (filter8)
     uint32_t pkeys[MMG_MAXL + 1];
     MmgCheck chk[MMG_MAXL];
     int32_t tab_key[MMG_MAXL];     // exact signed difference

@@ -125,59 +125,75 @@ __device__ __forceinline__ uint32_t diff_at(const uint32_t (&E)[8], const uint32
     return pair_at<POS>(E, O) - pair_at<POS - LB>(E, O) + 0x01000100u;      // halves: 256 + (cur - prv), never a borrow
 }
 
+// a - b as one IMAD (FMA pipe: the ALU pipe is the kernel's bottleneck)
+__device__ __forceinline__ uint32_t sub_fma(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(r) : "r"(b), "r"(a));
+    return r;
+}
+
 // Returns the 16-bit candidate mask of the lane: bit e <=> the element at the lane's own byte e is flagged.
 // NK > 0: compile-time key count.  DEPTH2 (simple / value-scan patterns, P.d2ok): a window whose comparison 0
 // PASSES (difference == keys[0]) is kept only if its comparison 1 -- the difference one element earlier -- is
 // a key as well; every other such window advances by J0 without a match, i.e. is not an event.
 template <int LB, int NK, bool DEPTH2>
 __device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t *x) {
+    // Odd lags: the pairs of odd bytes are unpacked WITH the bias (the PRMT takes the 0x01 bytes from its second source),
+    // so "current - previous" is a bare subtraction with a known constant in each half -- 256 + d for a biased current
+    // pair, d - 256 and d - 257 (the low half always borrows) for an unbiased one -- and runs as an IMAD on the idle FMA
+    // pipe.  The two kinds of difference register then use two sets of key constants (keys / pkeys).
+    constexpr bool FMA_DIFF = (LB & 1) != 0;
     uint32_t E[8], O[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { E[q] = x[q] & 0x00FF00FFu; O[q] = __byte_perm(x[q], 0u, 0x4341u); }
+    for (int q = 0; q < 8; q++) { E[q] = x[q] & 0x00FF00FFu; O[q] = __byte_perm(x[q], FMA_DIFF ? 0x01010101u : 0u, 0x4341u); }
     // D[1 + 2q + t]: pair (4q + t, 4q + t + 2) of the lane's own bytes; D[0]: pair (-3, -1) (DEPTH2 only)
     uint32_t D[9];
-    D[1] = diff_at<LB, 16>(E, O); D[2] = diff_at<LB, 17>(E, O); D[3] = diff_at<LB, 20>(E, O); D[4] = diff_at<LB, 21>(E, O);
-    D[5] = diff_at<LB, 24>(E, O); D[6] = diff_at<LB, 25>(E, O); D[7] = diff_at<LB, 28>(E, O); D[8] = diff_at<LB, 29>(E, O);
-    if (DEPTH2) D[0] = diff_at<LB, 13>(E, O);
+    if (FMA_DIFF) {
+        D[1] = sub_fma(pair_at<16>(E, O), pair_at<16 - LB>(E, O)); D[2] = sub_fma(pair_at<17>(E, O), pair_at<17 - LB>(E, O));
+        D[3] = sub_fma(pair_at<20>(E, O), pair_at<20 - LB>(E, O)); D[4] = sub_fma(pair_at<21>(E, O), pair_at<21 - LB>(E, O));
+        D[5] = sub_fma(pair_at<24>(E, O), pair_at<24 - LB>(E, O)); D[6] = sub_fma(pair_at<25>(E, O), pair_at<25 - LB>(E, O));
+        D[7] = sub_fma(pair_at<28>(E, O), pair_at<28 - LB>(E, O)); D[8] = sub_fma(pair_at<29>(E, O), pair_at<29 - LB>(E, O));
+        if (DEPTH2) D[0] = sub_fma(pair_at<13>(E, O), pair_at<13 - LB>(E, O));
+    } else {
+        D[1] = diff_at<LB, 16>(E, O); D[2] = diff_at<LB, 17>(E, O); D[3] = diff_at<LB, 20>(E, O); D[4] = diff_at<LB, 21>(E, O);
+        D[5] = diff_at<LB, 24>(E, O); D[6] = diff_at<LB, 25>(E, O); D[7] = diff_at<LB, 28>(E, O); D[8] = diff_at<LB, 29>(E, O);
+        if (DEPTH2) D[0] = diff_at<LB, 13>(E, O);
+    }
+    // key constant of difference register k: odd k holds an unbiased current pair (bytes 4q, 4q + 2)
+#define KEY8(j, k) ((FMA_DIFF && ((k) & 1)) ? P.pkeys[j] : P.keys[j])
     const int nk = NK > 0 ? NK : P.nkeys;
     uint32_t c[9];          // per half: 0 <=> candidate, else 1 (the min-accumulation starts from 1)
     if (!DEPTH2) {
-        const uint32_t k0 = P.keys[0];
 #pragma unroll
-        for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], k0, 0x00010001u);      // per-half add; halves stay in {0, 1}
+        for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], KEY8(0, k), 0x00010001u);      // per-half add; halves stay in {0, 1}
         if (NK > 0) {
 #pragma unroll
             for (int j = 1; j < NK; j++) {
-                const uint32_t kj = P.keys[j];
 #pragma unroll
-                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], kj, c[k]);
+                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], KEY8(j, k), c[k]);
             }
         } else {
 #pragma unroll 1
             for (int j = 1; j < nk; j++) {
-                const uint32_t kj = P.keys[j];
 #pragma unroll
-                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], kj, c[k]);
+                for (int k = 1; k < 9; k++) c[k] = __viaddmin_u16x2(D[k], KEY8(j, k), c[k]);
             }
         }
     } else {
         uint32_t ap[9], ao[9];      // pass key / the other keys
-        const uint32_t k0 = P.keys[0];
 #pragma unroll
-        for (int k = 0; k < 9; k++) { ap[k] = __viaddmin_u16x2(D[k], k0, 0x00010001u); ao[k] = 0x00010001u; }
+        for (int k = 0; k < 9; k++) { ap[k] = __viaddmin_u16x2(D[k], KEY8(0, k), 0x00010001u); ao[k] = 0x00010001u; }
         if (NK > 0) {
 #pragma unroll
             for (int j = 1; j < NK; j++) {
-                const uint32_t kj = P.keys[j];
 #pragma unroll
-                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], kj, ao[k]);
+                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], KEY8(j, k), ao[k]);
             }
         } else {
 #pragma unroll 1
             for (int j = 1; j < nk; j++) {
-                const uint32_t kj = P.keys[j];
 #pragma unroll
-                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], kj, ao[k]);
+                for (int k = 0; k < 9; k++) ao[k] = __viaddmin_u16x2(D[k], KEY8(j, k), ao[k]);
             }
         }
         // any[k]: zero half <=> that element's difference is some key
@@ -201,6 +217,7 @@ __device__ __forceinline__ uint32_t filter8(const MmgProgram &P, const uint32_t 
         m += c[2 * q + 1] << (4 * q);
         m += c[2 * q + 2] << (4 * q + 1);
     }
+#undef KEY8
     return ((m | (m >> 14)) & 0xFFFFu) ^ 0xFFFFu;
 }
 
@@ -752,7 +769,9 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const int ev_nc = P.ncheck;
     const uint32_t ev_pmask = VP.pmask, ev_o1c = VP.o1c, ev_o1p = VP.o1p, ev_match = VP.matchword;
     const uint32_t sprog_a = smem_u32(&g_sprog);
-    const uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
+    uint32_t tab0_a = sprog_a + (uint32_t)offsetof(SProg, tab0) + 255u, tab1_a = sprog_a + (uint32_t)offsetof(SProg, tab1) + 255u;
+    // keep the table addresses in registers: left alone, ptxas re-derives the shared window base for every candidate
+    asm volatile("" : "+r"(tab0_a), "+r"(tab1_a));
     const uint32_t lt = (1u << lane) - 1u;
     const bool d2ok = P.d2ok != 0;
 
@@ -825,10 +844,10 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             const bool dense = dense_left != 0;
             const uint32_t rows = min(MMG_STAGE8 / MMG_ROW8, (len - rel_stage + MMG_ROW8 - 1) / MMG_ROW8);
             uint32_t stage_cands = 0;
+            uint32_t sa = stage_a + (uint32_t)lane * 32u;                               // the 16 bytes before the lane's own 32
+            uint32_t rowrel = rel_stage;
 #pragma unroll 1
-            for (uint32_t r = 0; r < rows; r++) {
-                const uint32_t rowrel = rel_stage + r * MMG_ROW8;
-                const uint32_t sa = stage_a + r * MMG_ROW8 + (uint32_t)lane * 32u;      // the 16 bytes before the lane's own 32
+            for (uint32_t r = 0; r < rows; r++, sa += MMG_ROW8, rowrel += MMG_ROW8) {
                 const uint32_t lanerel = rowrel + (uint32_t)lane * 32u;
                 uint32_t x[12];
                 {
@@ -1289,11 +1308,170 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     if (s_last) {
         __threadfence();
         if (tid < 4) X.host_status[tid] = reinterpret_cast<volatile uint64_t *>(X.status)[tid];
+        if (tid == 4) X.host_status[4] = 0;                       // (k_resolve_sparse reports "too dense" here)
         __threadfence_system();
         __syncthreads();
         if (tid < 4) X.status[tid] = 0;
         if (tid < 2) X.ticket[tid] = 0;
         for (uint32_t i = tid; i < G.nseg; i += RESOLVE_THREADS) X.lookback[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2s: resolve for SPARSE scans -- one WARP per engine block, direct replay, no maps.
+// A pattern like cfg2's leaves a handful of events per 512 KiB block.  k_resolve spends a CTA of 128 threads and some
+// ten block-wide barriers on each block whatever it holds; here a warp gathers the (few) events of its block into shared
+// memory with three rounds of independent loads, replays the block's chains through them once -- positions are
+// absolute within the block, so "is this event visited" is a plain lattice test and no per-sub-tile phase is needed --
+// takes the block's base in the output from the same decoupled look-back, and writes the matches.  A block with more
+// events than the staging area holds raises a flag; the host then runs k_resolve over the same event lists.
+// ------------------------------------------------------------------------------------------
+
+#define SPARSE_WARPS 8
+#define SPARSE_EV_CAP 1024u
+
+template <int W, bool BE>
+__global__ void __launch_bounds__(SPARSE_WARPS * 32)
+k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
+                 uint64_t *out_off, uint32_t *out_val, uint64_t capacity) {
+    __shared__ uint32_t s_ev[SPARSE_WARPS][SPARSE_EV_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *sm = s_ev[wid];
+    const bool bad = events_overflowed(X);
+
+    // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
+    uint32_t bi = 0;
+    if (lane == 0) bi = atomicAdd(X.ticket, 1u);
+    bi = __shfl_sync(FULL, bi, 0);
+    if (bi < G.nblocks) {
+        uint32_t m = 0;                                       // matches of this block
+        const uint32_t t0 = bi * G.spb;
+        const uint32_t nsb = bad ? 0u : min(G.spb, G.nsub - t0);          // sub-tiles of this block (<= 128)
+        // round 1: has-events flags of the lane's four sub-tiles; round 2: their list extents
+        uint32_t st[4], cn[4], mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = 4u * (uint32_t)lane + (uint32_t)k;
+            cn[k] = (j < nsb && X.hasev[t0 + j] != 0) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = t0 + 4u * (uint32_t)lane + (uint32_t)k;
+            st[k] = cn[k] ? X.sub_start[t] : 0u;
+            cn[k] = cn[k] ? X.sub_count[t] : 0u;
+            mine += cn[k];
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t n = __shfl_sync(FULL, incl, 31);
+        if (n > SPARSE_EV_CAP) {
+            if (lane == 0) atomicOr(X.ticket + 2, 1u);        // too dense for this kernel: the host falls back to k_resolve
+        } else if (n != 0) {
+            // round 3: the events, as  byte offset in the block [18:0] | advance [26:19] | match [27]
+            uint32_t at = incl - mine;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t base = (4u * (uint32_t)lane + (uint32_t)k) << MMG_SUBTILE_SHIFT;
+                for (uint32_t j = 0; j < cn[k]; j++) {
+                    const uint32_t w = X.ev[st[k] + j];
+                    sm[at++] = (base + MMG_EV_OFF(w)) | (MMG_EV_JUMP(w) << 19) | ((w & MMG_EV_MATCH) ? (1u << 27) : 0u);
+                }
+            }
+            __syncwarp();
+            // replay, every lane the same: the chains of the block's alignment classes start at its first element
+            const uint32_t J0 = P.J0;
+            const uint32_t magic = 0xFFFFFFFFu / J0 + 1u;      // floor(2^32 / J0) + 1 (2^32 / J0 for powers of two): exact quotients for dividends < 2^19
+            uint32_t xc[2] = {0u, 0u};
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t e = sm[i];
+                const uint32_t bo = e & 0x7FFFFu;
+                const uint32_t c = (W == 2) ? (bo & 1u) : 0u;
+                const uint32_t q = bo / W, x = xc[c];
+                if (x <= q) {
+                    const uint32_t d = q - x;
+                    if (J0 == 1u || d - __umulhi(d, magic) * J0 == 0u) {
+                        xc[c] = q + ((e >> 19) & 0xFFu);
+                        if (e & (1u << 27)) {
+                            __syncwarp();
+                            if (lane == 0) sm[m] = bo;        // m <= i: never ahead of the read position
+                            m++;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // base of this block in the output: decoupled look-back, 8 x 32 predecessors per step
+        volatile uint64_t *lb = X.lookback;
+        uint64_t before = 0;
+        if (bi > 0) {
+            if (lane == 0) lb[bi] = LB_AGG | m;
+            int64_t hi = (int64_t)bi - 1;
+            bool finished = false;
+            while (!finished) {
+                uint64_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int64_t j = hi - 32 * k - lane;
+                    v[k] = j >= 0 ? lb[j] : LB_INCL;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t flag = (uint32_t)(v[k] >> 62);
+                    const uint32_t inclm = __ballot_sync(FULL, flag == 2);
+                    const uint32_t stop = inclm ? (uint32_t)__ffs(inclm) - 1 : 32u;
+                    const uint32_t need = stop == 32 ? FULL : ((2u << stop) - 1u);
+                    if (__ballot_sync(FULL, flag == 0) & need) break;
+                    uint64_t part = (lane <= (int)stop) ? (v[k] & LB_MASK) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                    before += part;
+                    hi -= 32;
+                    if (stop < 32) { finished = true; break; }
+                }
+            }
+        }
+        if (lane == 0) {
+            lb[bi] = LB_INCL | (before + m);
+            if (bi == G.nblocks - 1) X.status[2] = before + m;
+        }
+        // emission
+        const uint64_t blk_off = (uint64_t)bi * G.B;
+        const uint32_t o0 = (uint32_t)P.first_lit * W;
+        const bool has1 = P.opp_idx >= 0;
+        const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
+        for (uint32_t i = lane; i < m; i += 32) {
+            if (before + i >= capacity) break;
+            const uint64_t sb = blk_off + sm[i];
+            uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
+            if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
+            out_off[before + i] = (G.base_offset + sb) >> G.report_shift;
+            out_val[before + i] = v;
+        }
+    }
+
+    // the last CTA to finish hands the status words to the host and restores the all-zero state of the workspace
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(X.ticket + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x < 4) X.host_status[threadIdx.x] = reinterpret_cast<volatile uint64_t *>(X.status)[threadIdx.x];
+        if (threadIdx.x == 4) X.host_status[4] = reinterpret_cast<volatile uint32_t *>(X.ticket)[2];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < 4) X.status[threadIdx.x] = 0;
+        if (threadIdx.x < 3) X.ticket[threadIdx.x] = 0;
+        for (uint32_t i = threadIdx.x; i < G.nseg; i += blockDim.x) X.lookback[i] = 0;
     }
 }
 
@@ -1592,6 +1770,17 @@ cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgS
     if (P.W == 1) k_resolve<1, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     else if (G.big_endian) k_resolve<2, true, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     else k_resolve<2, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    return cudaGetLastError();
+}
+
+bool mmg_sparse_resolve_supported(const MmgGeom &G) { return G.segs_per_block == 1 && G.spb <= 128; }
+
+cudaError_t mmg_launch_resolve_sparse(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                                      uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    const unsigned grid = (G.nblocks + SPARSE_WARPS - 1) / SPARSE_WARPS;
+    if (P.W == 1) k_resolve_sparse<1, false><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
+    else if (G.big_endian) k_resolve_sparse<2, true><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
+    else k_resolve_sparse<2, false><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
     return cudaGetLastError();
 }
 

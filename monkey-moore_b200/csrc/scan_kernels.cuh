@@ -70,7 +70,8 @@ struct MmgScratch {
                            // [2] total matches [3] next chunk (dynamic scheduling)
     uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts
     uint32_t *ticket;      // [0] block ticket of the resolve kernel  [1] CTAs of the resolve kernel that are done
-    uint64_t *host_status; // pinned, device-visible: receives status[0..3] when the resolve kernel ends
+                           // [2] k_resolve_sparse: a block held more events than it can stage
+    uint64_t *host_status; // pinned, device-visible: receives status[0..3] (+ [4] = ticket[2]) when the resolve kernel ends
     uint8_t *segmap;       // [nseg][2][jp] entry phase -> exit phase of a whole segment (only when segs_per_block > 1)
     uint8_t *segphase;     // [nseg][2] entry phase of the segment
 };
