@@ -46,7 +46,7 @@ _i16p = C.POINTER(C.c_int16)
 class ScanStats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_filter", C.c_float), ("ms_h2d", C.c_float),
                 ("launches", C.c_uint32), ("fast_path", C.c_uint32), ("events", C.c_uint64),
-                ("bytes_scanned", C.c_uint64)]
+                ("bytes_scanned", C.c_uint64), ("resolve_kind", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class MMError(RuntimeError):

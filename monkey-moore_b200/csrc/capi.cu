@@ -289,9 +289,8 @@ void enqueue_tiled(mmg_results *res) {
     const size_t o_lookback = carve((size_t)G.nseg * sizeof(uint64_t));
     const size_t zero_need = off;
     off = 0;
-    const size_t o_hasev = carve((size_t)G.nsub);
-    const size_t o_start = carve((size_t)G.nsub * sizeof(uint32_t));
-    const size_t o_count = carve((size_t)G.nsub * sizeof(uint32_t));
+    const size_t o_ext = carve((size_t)G.nsub * sizeof(uint2));
+    const size_t o_brec = carve((size_t)G.nblocks * 32 * sizeof(uint32_t));
     const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
     const size_t jp = (size_t)((P.Jmax + 15) / 16 * 16);
@@ -309,9 +308,8 @@ void enqueue_tiled(mmg_results *res) {
     X.status = reinterpret_cast<uint64_t *>(ws.zero + o_status);
     X.ticket = reinterpret_cast<uint32_t *>(ws.zero + o_ticket);
     X.lookback = reinterpret_cast<uint64_t *>(ws.zero + o_lookback);
-    X.hasev = ws.scratch + o_hasev;
-    X.sub_start = reinterpret_cast<uint32_t *>(ws.scratch + o_start);
-    X.sub_count = reinterpret_cast<uint32_t *>(ws.scratch + o_count);
+    X.ext = reinterpret_cast<uint2 *>(ws.scratch + o_ext);
+    X.brec = reinterpret_cast<uint32_t *>(ws.scratch + o_brec);
     X.mcount = reinterpret_cast<uint32_t *>(ws.scratch + o_mcount);
     X.mbase = reinterpret_cast<uint64_t *>(ws.scratch + o_mbase);
     X.segmap = ws.scratch + o_segmap;
@@ -419,6 +417,7 @@ void finish_tiled(mmg_results *res) {
         // (the zero state was restored, the lists are intact unless another scan used the workspace since)
         std::lock_guard<std::mutex> lock(res->dev->mu);
         t.sparse = false;
+        res->stats.resolve_kind = 2;
         if (t.generation == t.ws->generation) {
             CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
             res->launches += t.G.segs_per_block > 1 ? 3 : 1;
@@ -430,6 +429,7 @@ void finish_tiled(mmg_results *res) {
         CU(cudaEventRecord(res->ev[3], stream));
         CU(cudaStreamSynchronize(stream));
     }
+    if (t.sparse) res->stats.resolve_kind = 1;
     res->rq.prog->last_events_per_warp = ev_max;
     res->rq.prog->last_events = ev_total;
     res->rq.prog->last_bytes = res->rq.S;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -301,18 +302,11 @@ struct WarpState {
 };
 
 __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState st, uint32_t t, int lane) {
-    // every sub-tile the warp passes gets its has-events flag (the resolve kernel reads it without any zeroing
-    // by the host); extents are recorded only where events exist
+    // every sub-tile the warp passes gets its extent word {first event, number of events} -- a count of 0 where it has
+    // none, so the resolve kernels read the extents without any zeroing by the host
     if (st.open_t < t) {
-        const bool has = st.cursor != st.open_start;
-        if (lane == 0) {
-            if (has) {
-                X.sub_start[st.open_t] = st.open_start;
-                X.sub_count[st.open_t] = st.cursor - st.open_start;
-            }
-            X.hasev[st.open_t] = has ? 1 : 0;
-        }
-        for (uint32_t u = st.open_t + 1 + (uint32_t)lane; u < t; u += 32) X.hasev[u] = 0;      // passed without events
+        if (lane == 0) X.ext[st.open_t] = make_uint2(st.open_start, st.cursor - st.open_start);
+        for (uint32_t u = st.open_t + 1 + (uint32_t)lane; u < t; u += 32) X.ext[u] = make_uint2(0u, 0u);      // passed without events
         st.open_start = st.cursor;
         st.open_t = t;
     }
@@ -546,14 +540,7 @@ __device__ __noinline__ uint32_t eval_window_lds8(uint32_t wa, uint32_t sp, int 
 
 // record the extent of sub-tile t's event list: [st.open_start, cut)
 __device__ __forceinline__ WarpState close_at(const MmgScratch &X, WarpState st, uint32_t t, uint32_t cut, int lane) {
-    if (lane == 0) {
-        const bool has = cut != st.open_start;
-        if (has) {
-            X.sub_start[t] = st.open_start;
-            X.sub_count[t] = cut - st.open_start;
-        }
-        X.hasev[t] = has ? 1 : 0;       // written for every sub-tile: nothing to zero before a scan
-    }
+    if (lane == 0) X.ext[t] = make_uint2(st.open_start, cut - st.open_start);       // written for every sub-tile: nothing to zero before a scan
     st.open_start = cut;
     st.open_t = t + 1;
     return st;
@@ -960,8 +947,9 @@ __device__ __forceinline__ uint32_t lattice_advance(uint32_t x, uint32_t n, uint
 template <int W, bool BE>
 __device__ __forceinline__ void emit_subtile(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t t,
                                              uint64_t at, uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_val) {
-    const uint32_t n = X.sub_count[t];
-    const uint32_t *__restrict__ ev = X.ev + X.sub_start[t];
+    const uint2 ext = X.ext[t];
+    const uint32_t n = ext.y;
+    const uint32_t *__restrict__ ev = X.ev + ext.x;
     const uint8_t *__restrict__ data = G.data;
     const uint32_t o0 = (uint32_t)P.first_lit * W;
     const bool has1 = P.opp_idx >= 0;
@@ -1043,7 +1031,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 
     for (uint32_t tb = t_begin; tb < t_end && !bad; tb += RESOLVE_THREADS) {
         const uint32_t t = tb + tid;
-        const bool he = t < t_end && X.hasev[t] != 0;
+        const uint2 ext = t < t_end ? X.ext[t] : make_uint2(0u, 0u);
+        const bool he = ext.y != 0;
         const uint32_t nvalid = min((uint32_t)RESOLVE_THREADS, t_end - tb);
         if (!__syncthreads_or(he)) {
             if (MAPS_ONLY) {            // no events in the whole segment: every entry phase just follows its lattice
@@ -1061,8 +1050,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         uint32_t *ev = nullptr;
         s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0;
         if (he && fast) {
-            n = X.sub_count[t];
-            ev = X.ev + X.sub_start[t];
+            n = ext.y;
+            ev = X.ev + ext.x;
             const uint32_t base = NP % J0;
             for (uint32_t c = 0; c < npads; c++)
                 for (uint32_t r = 0; r < J0; r++)      // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0
@@ -1100,8 +1089,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             }
             s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
         } else if (he) {
-            n = X.sub_count[t];
-            ev = X.ev + X.sub_start[t];
+            n = ext.y;
+            ev = X.ev + ext.x;
             for (uint32_t c = 0; c < npads; c++) {
                 uint32_t x[MMG_MAXL];
                 for (uint32_t e = 0; e < Jmax; e++) x[e] = e;
@@ -1275,7 +1264,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         uint64_t running = s_before;
         for (uint32_t tb = t_begin; tb < t_end; tb += RESOLVE_THREADS) {
             const uint32_t t = tb + tid;
-            const bool he = t < t_end && X.hasev[t] != 0;
+            const bool he = t < t_end && X.ext[t].y != 0;
             const uint32_t cnt = he ? X.mcount[t] : 0u;
             uint32_t incl = cnt;
 #pragma unroll
@@ -1318,48 +1307,46 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
 }
 
 // ------------------------------------------------------------------------------------------
-// K2s: resolve for SPARSE scans -- one WARP per engine block, direct replay, no maps.
+// K2s: resolve for SPARSE scans -- one WARP per engine block, direct replay, no maps, no look-back.
 // A pattern like cfg2's leaves a handful of events per 512 KiB block.  k_resolve spends a CTA of 128 threads and some
-// ten block-wide barriers on each block whatever it holds; here a warp gathers the (few) events of its block into shared
-// memory with three rounds of independent loads, replays the block's chains through them once -- positions are
-// absolute within the block, so "is this event visited" is a plain lattice test and no per-sub-tile phase is needed --
-// takes the block's base in the output from the same decoupled look-back, and writes the matches.  A block with more
-// events than the staging area holds raises a flag; the host then runs k_resolve over the same event lists.
+// ten block-wide barriers on each block whatever it holds, and its decoupled look-back keeps a thousand nearly idle
+// CTAs spinning on each other.  Here a warp reads the extent words of its block's sub-tiles (one round of loads), the
+// few events behind them (a second round), replays the block's chains through them once -- positions are absolute
+// within the block, so "is this event visited" is a plain lattice test and no per-sub-tile phase is needed -- and leaves
+// the block's matches in a small per-block record.  The LAST CTA to finish turns the per-block counts into output
+// positions and writes the (few) matches in file order.  A block with more events, or more matches, than its record
+// holds raises a flag; the host then runs k_resolve over the same event lists.
 // ------------------------------------------------------------------------------------------
 
 #define SPARSE_WARPS 8
 #define SPARSE_EV_CAP 1024u
+#define SPARSE_REC 32u          // words of a block record: [0] match count, [1..31] byte offsets of the matches in the block
 
 template <int W, bool BE>
 __global__ void __launch_bounds__(SPARSE_WARPS * 32)
 k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
                  uint64_t *out_off, uint32_t *out_val, uint64_t capacity) {
     __shared__ uint32_t s_ev[SPARSE_WARPS][SPARSE_EV_CAP];
+    __shared__ uint32_t s_last;
+    __shared__ uint64_t s_scan[SPARSE_WARPS];
+    __shared__ uint64_t s_carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *sm = s_ev[wid];
     const bool bad = events_overflowed(X);
+    const uint32_t bi = blockIdx.x * SPARSE_WARPS + (uint32_t)wid;
 
-    // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
-    uint32_t bi = 0;
-    if (lane == 0) bi = atomicAdd(X.ticket, 1u);
-    bi = __shfl_sync(FULL, bi, 0);
     if (bi < G.nblocks) {
         uint32_t m = 0;                                       // matches of this block
         const uint32_t t0 = bi * G.spb;
         const uint32_t nsb = bad ? 0u : min(G.spb, G.nsub - t0);          // sub-tiles of this block (<= 128)
-        // round 1: has-events flags of the lane's four sub-tiles; round 2: their list extents
-        uint32_t st[4], cn[4], mine = 0;
+        // round 1: the extent words of the lane's four sub-tiles
+        uint2 ex[4];
+        uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t j = 4u * (uint32_t)lane + (uint32_t)k;
-            cn[k] = (j < nsb && X.hasev[t0 + j] != 0) ? 1u : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t t = t0 + 4u * (uint32_t)lane + (uint32_t)k;
-            st[k] = cn[k] ? X.sub_start[t] : 0u;
-            cn[k] = cn[k] ? X.sub_count[t] : 0u;
-            mine += cn[k];
+            ex[k] = j < nsb ? X.ext[t0 + j] : make_uint2(0u, 0u);
+            mine += ex[k].y;
         }
         uint32_t incl = mine;
 #pragma unroll
@@ -1368,23 +1355,22 @@ k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ M
             if (lane >= o) incl += v;
         }
         const uint32_t n = __shfl_sync(FULL, incl, 31);
-        if (n > SPARSE_EV_CAP) {
-            if (lane == 0) atomicOr(X.ticket + 2, 1u);        // too dense for this kernel: the host falls back to k_resolve
-        } else if (n != 0) {
-            // round 3: the events, as  byte offset in the block [18:0] | advance [26:19] | match [27]
+        bool dense = n > SPARSE_EV_CAP;
+        if (!dense && n != 0) {
+            // round 2: the events, as  byte offset in the block [18:0] | advance [26:19] | match [27]
             uint32_t at = incl - mine;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t base = (4u * (uint32_t)lane + (uint32_t)k) << MMG_SUBTILE_SHIFT;
-                for (uint32_t j = 0; j < cn[k]; j++) {
-                    const uint32_t w = X.ev[st[k] + j];
+                for (uint32_t j = 0; j < ex[k].y; j++) {
+                    const uint32_t w = X.ev[ex[k].x + j];
                     sm[at++] = (base + MMG_EV_OFF(w)) | (MMG_EV_JUMP(w) << 19) | ((w & MMG_EV_MATCH) ? (1u << 27) : 0u);
                 }
             }
             __syncwarp();
             // replay, every lane the same: the chains of the block's alignment classes start at its first element
             const uint32_t J0 = P.J0;
-            const uint32_t magic = 0xFFFFFFFFu / J0 + 1u;      // floor(2^32 / J0) + 1 (2^32 / J0 for powers of two): exact quotients for dividends < 2^19
+            const uint32_t magic = 0xFFFFFFFFu / J0 + 1u;     // floor(2^32 / J0) + 1 (2^32 / J0 for powers of two): exact quotients below 2^19
             uint32_t xc[2] = {0u, 0u};
             for (uint32_t i = 0; i < n; i++) {
                 const uint32_t e = sm[i];
@@ -1396,7 +1382,7 @@ k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ M
                     if (J0 == 1u || d - __umulhi(d, magic) * J0 == 0u) {
                         xc[c] = q + ((e >> 19) & 0xFFu);
                         if (e & (1u << 27)) {
-                            __syncwarp();
+                            __syncwarp();                     // every lane has read entry i
                             if (lane == 0) sm[m] = bo;        // m <= i: never ahead of the read position
                             m++;
                         }
@@ -1404,75 +1390,65 @@ k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ M
                 }
             }
             __syncwarp();
+            dense = m >= SPARSE_REC;
         }
+        if (dense) {
+            if (lane == 0) atomicOr(X.ticket + 2, 1u);        // not sparse after all: the host falls back to k_resolve
+            m = 0;
+        }
+        uint32_t *rec = X.brec + (size_t)bi * SPARSE_REC;
+        if (lane == 0) rec[0] = m;
+        if (lane < (int)m) rec[1 + lane] = sm[lane];
+    }
 
-        // base of this block in the output: decoupled look-back, 8 x 32 predecessors per step
-        volatile uint64_t *lb = X.lookback;
-        uint64_t before = 0;
-        if (bi > 0) {
-            if (lane == 0) lb[bi] = LB_AGG | m;
-            int64_t hi = (int64_t)bi - 1;
-            bool finished = false;
-            while (!finished) {
-                uint64_t v[8];
+    // ---- the last CTA to finish: output positions (prefix over the block counts), emission, status, zero state
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(X.ticket + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t o0 = (uint32_t)P.first_lit * W;
+    const bool has1 = P.opp_idx >= 0;
+    const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
+    const volatile uint32_t *brec = X.brec;
+    for (uint32_t b0 = 0; b0 < G.nblocks; b0 += SPARSE_WARPS * 32) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t cnt = b < G.nblocks ? brec[(size_t)b * SPARSE_REC] : 0u;
+        uint64_t incl = cnt;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int64_t j = hi - 32 * k - lane;
-                    v[k] = j >= 0 ? lb[j] : LB_INCL;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t flag = (uint32_t)(v[k] >> 62);
-                    const uint32_t inclm = __ballot_sync(FULL, flag == 2);
-                    const uint32_t stop = inclm ? (uint32_t)__ffs(inclm) - 1 : 32u;
-                    const uint32_t need = stop == 32 ? FULL : ((2u << stop) - 1u);
-                    if (__ballot_sync(FULL, flag == 0) & need) break;
-                    uint64_t part = (lane <= (int)stop) ? (v[k] & LB_MASK) : 0ull;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-                    before += part;
-                    hi -= 32;
-                    if (stop < 32) { finished = true; break; }
-                }
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
         }
-        if (lane == 0) {
-            lb[bi] = LB_INCL | (before + m);
-            if (bi == G.nblocks - 1) X.status[2] = before + m;
-        }
-        // emission
-        const uint64_t blk_off = (uint64_t)bi * G.B;
-        const uint32_t o0 = (uint32_t)P.first_lit * W;
-        const bool has1 = P.opp_idx >= 0;
-        const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
-        for (uint32_t i = lane; i < m; i += 32) {
-            if (before + i >= capacity) break;
-            const uint64_t sb = blk_off + sm[i];
+        if (lane == 31) s_scan[wid] = incl;
+        __syncthreads();
+        uint64_t wbase = s_carry, tile = 0;
+        for (int i = 0; i < SPARSE_WARPS; i++) { if (i < wid) wbase += s_scan[i]; tile += s_scan[i]; }
+        uint64_t at = wbase + incl - cnt;
+        const uint64_t blk_off = (uint64_t)b * G.B;
+        for (uint32_t i = 0; i < cnt && at < capacity; i++, at++) {
+            const uint64_t sb = blk_off + brec[(size_t)b * SPARSE_REC + 1 + i];
             uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
             if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
-            out_off[before + i] = (G.base_offset + sb) >> G.report_shift;
-            out_val[before + i] = v;
+            out_off[at] = (G.base_offset + sb) >> G.report_shift;
+            out_val[at] = v;
         }
-    }
-
-    // the last CTA to finish hands the status words to the host and restores the all-zero state of the workspace
-    __shared__ uint32_t s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(X.ticket + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        if (threadIdx.x < 4) X.host_status[threadIdx.x] = reinterpret_cast<volatile uint64_t *>(X.status)[threadIdx.x];
-        if (threadIdx.x == 4) X.host_status[4] = reinterpret_cast<volatile uint32_t *>(X.ticket)[2];
-        __threadfence_system();
         __syncthreads();
-        if (threadIdx.x < 4) X.status[threadIdx.x] = 0;
-        if (threadIdx.x < 3) X.ticket[threadIdx.x] = 0;
-        for (uint32_t i = threadIdx.x; i < G.nseg; i += blockDim.x) X.lookback[i] = 0;
+        if (threadIdx.x == 0) s_carry += tile;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) X.status[2] = s_carry;
+    __syncthreads();
+    __threadfence();
+    if (threadIdx.x < 4) X.host_status[threadIdx.x] = reinterpret_cast<volatile uint64_t *>(X.status)[threadIdx.x];
+    if (threadIdx.x == 4) X.host_status[4] = reinterpret_cast<volatile uint32_t *>(X.ticket)[2];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 4) X.status[threadIdx.x] = 0;
+    if (threadIdx.x < 3) X.ticket[threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1577,7 +1553,7 @@ __global__ void __launch_bounds__(128)
 k_emit(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
        uint64_t *out_off, uint32_t *out_val) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G.nsub || !X.hasev[t]) return;
+    if (t >= G.nsub || X.ext[t].y == 0) return;
     if (X.mcount[t] == 0) return;
     emit_subtile<W, BE>(P, G, X, t, X.mbase[t], out_off, out_val);
 }

@@ -59,11 +59,10 @@ struct MmgGeom {
 struct MmgScratch {
     uint32_t *ev;          // event words, one private region per filter warp
     uint32_t ev_per_warp;
-    uint8_t *hasev;        // [nsub] sub-tile owns events (written for every sub-tile by the filter)
-    uint32_t *sub_start;   // [nsub] first event of the sub-tile (valid where hasev)
-    uint32_t *sub_count;   // [nsub] ditto
-    uint32_t *mcount;      // [nsub] visited matches (valid where hasev)
-    uint64_t *mbase;       // [nsub] position of the sub-tile's first match in the output (valid where hasev)
+    uint2 *ext;            // [nsub] {first event, number of events} of the sub-tile, written for EVERY sub-tile by the filter
+    uint32_t *mcount;      // [nsub] visited matches (valid where the sub-tile has events)
+    uint64_t *mbase;       // [nsub] position of the sub-tile's first match in the output (ditto)
+    uint32_t *brec;        // [nblocks][32] k_resolve_sparse: per-block record {match count, byte offsets of the matches}
     // Zero state: all zero when a scan starts.  The last CTA of the resolve kernel to finish copies `status` to the
     // host's pinned slot and zeroes it all again, so a workspace serves scan after scan without a memset.
     uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events

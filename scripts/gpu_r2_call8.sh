@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/c8_gpu_tests.log 2>&1; echo "pytest rc=$?" >> $O/c8_gpu_tests.log
+timeout 300 python scripts/perf_probe.py 512 > $O/c8_probe.txt 2>&1
+MMG_NO_SPARSE_RESOLVE=1 PROBE_CASES="16" timeout 300 python scripts/perf_probe.py 512 > $O/c8_probe_nosparse.txt 2>&1
+tail -3 $O/c8_gpu_tests.log; cat $O/c8_probe.txt $O/c8_probe_nosparse.txt

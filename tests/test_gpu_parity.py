@@ -179,3 +179,44 @@ def test_engine_big_blocks(gpu, seed):
         be = bool(rng.random() < 0.4)
         hits += check_engine(gpu, bits, pat, fb, block, be)
     assert hits > 0
+
+
+def test_sparse_resolve_kernel_and_its_fallback(gpu):
+    """The second scan of a pattern whose first scan left few events per block is resolved by the warp-per-block kernel;
+    a later scan over dense data makes that kernel hand over to the general one.  Results stay bit-exact throughout."""
+    rng = np.random.default_rng(77)
+    sparse = rng.integers(0, 256, size=3 << 20, dtype=np.uint8)
+    for v in (10, 100000, 2000000, (3 << 20) - 9):          # planted 8-bit matches, one right before the end
+        sparse[v:v + 6] = np.frombuffer(b"monkey", dtype=np.uint8) + 3
+    sparse[524288 - 3:524288 + 3] = np.frombuffer(b"monkey", dtype=np.uint8)
+
+    def dense16(be):        # 16-bit elements from an 8-symbol alphabet: every ninth difference is +1
+        e = rng.integers(100, 108, size=3 << 19, dtype=np.uint16)
+        return np.ascontiguousarray(e.byteswap() if be else e).view(np.uint8)
+
+    def planted16(be):      # sparse 16-bit data with shifted copies of "abcde", aligned and odd, one across a block edge
+        b = sparse.copy()
+        for v in (64, 70001, 524288 - 4, 1500000, 2999990):
+            e = (np.array([0x4100, 0x4101, 0x4102, 0x4103, 0x4104], dtype=np.uint16) + np.uint16(v % 97))
+            b[v:v + 10] = np.ascontiguousarray(e.byteswap() if be else e).view(np.uint8)
+        return b
+
+    cases = [(8, dict(keyword="monkey"), False, sparse, rng.integers(0, 4, size=3 << 20, dtype=np.uint8), False),
+             (16, dict(keyword="mo*key*s", wildcard=ord("*")), False, sparse, dense16(False), False),
+             (16, dict(keyword="abcde"), False, planted16(False), dense16(False), True),
+             (16, dict(keyword="abcde"), True, planted16(True), dense16(True), True)]
+    for bits, pat, be, few, many, expect_handover in cases:
+        prog = gpu.Program(bits, **pat)
+        o = Oracle(bits, **pat_kwargs(pat))
+        kinds, counts = [], []
+        for blob in (few, few, many, few, few):
+            res = prog.engine_scan(blob, 524288, big_endian=be)
+            off, val = res.arrays()
+            kinds.append(res.stats()["resolve_kind"])
+            counts.append(len(off))
+            exp, expv = o.engine(blob, 524288, big_endian=be, wrap32=False)
+            assert off.tolist() == exp.tolist() and val.tolist() == expv.tolist(), (bits, pat, be, kinds)
+        assert kinds[0] == 0, kinds                       # no hint yet: general kernel
+        if expect_handover:                               # sparse, handed over on dense data, general, sparse again
+            assert kinds == [0, 1, 2, 0, 1], (kinds, counts)
+            assert counts[0] >= 3, counts
