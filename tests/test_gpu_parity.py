@@ -194,17 +194,17 @@ def test_sparse_resolve_kernel_and_its_fallback(gpu):
         e = rng.integers(100, 108, size=3 << 19, dtype=np.uint16)
         return np.ascontiguousarray(e.byteswap() if be else e).view(np.uint8)
 
-    def planted16(be):      # sparse 16-bit data with shifted copies of "abcde", aligned and odd, one across a block edge
+    def planted16(be):      # sparse 16-bit data with shifted copies of "acegh", aligned and odd, one across a block edge
         b = sparse.copy()
         for v in (64, 70001, 524288 - 4, 1500000, 2999990):
-            e = (np.array([0x4100, 0x4101, 0x4102, 0x4103, 0x4104], dtype=np.uint16) + np.uint16(v % 97))
+            e = (np.array([0x4100, 0x4102, 0x4104, 0x4106, 0x4107], dtype=np.uint16) + np.uint16(v % 97))
             b[v:v + 10] = np.ascontiguousarray(e.byteswap() if be else e).view(np.uint8)
         return b
 
     cases = [(8, dict(keyword="monkey"), False, sparse, rng.integers(0, 4, size=3 << 20, dtype=np.uint8), False),
              (16, dict(keyword="mo*key*s", wildcard=ord("*")), False, sparse, dense16(False), False),
-             (16, dict(keyword="abcde"), False, planted16(False), dense16(False), True),
-             (16, dict(keyword="abcde"), True, planted16(True), dense16(True), True)]
+             (16, dict(keyword="acegh"), False, planted16(False), dense16(False), True),
+             (16, dict(keyword="acegh"), True, planted16(True), dense16(True), True)]
     for bits, pat, be, few, many, expect_handover in cases:
         prog = gpu.Program(bits, **pat)
         o = Oracle(bits, **pat_kwargs(pat))
@@ -219,4 +219,4 @@ def test_sparse_resolve_kernel_and_its_fallback(gpu):
         assert kinds[0] == 0, kinds                       # no hint yet: general kernel
         if expect_handover:                               # sparse, handed over on dense data, general, sparse again
             assert kinds == [0, 1, 2, 0, 1], (kinds, counts)
-            assert counts[0] >= 3, counts
+            assert counts[0] >= 2, counts
