@@ -135,7 +135,7 @@ typedef struct mmg_scan_stats {
     uint32_t fast_path;      /* 1 = tiled streaming path, 0 = generic per-chain path */
     uint64_t events;         /* candidate windows that needed exact evaluation */
     uint64_t bytes_scanned;
-    uint32_t resolve_kind;   /* 0 general resolve kernel, 1 warp-per-block kernel for sparse scans, 2 sparse tried, general re-run */
+    uint32_t resolve_kind;   /* 0 resolve kernel, 1 resolved inside the filter kernel (sparse scans), 2 that was tried and the resolve kernel re-ran */
     uint32_t reserved;
 } mmg_scan_stats;
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);

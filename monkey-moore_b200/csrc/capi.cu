@@ -149,7 +149,7 @@ struct TiledState {
     MmgGeom G{};
     MmgScratch X{};
     int lag_bytes = 0, grid = 0;
-    bool sparse = false;          // resolved by k_resolve_sparse (one warp per block): no per-sub-tile match bookkeeping exists
+    bool sparse = false;          // resolved inside the filter kernel (fused sparse resolve): no per-sub-tile match bookkeeping exists
     uint64_t total_warps = 0, per_warp = 0, cap = 0;
     uint64_t generation = 0;      // workspace generation of this scan's last enqueue
     Workspace *ws = nullptr;
@@ -291,6 +291,7 @@ void enqueue_tiled(mmg_results *res) {
     off = 0;
     const size_t o_ext = carve((size_t)G.nsub * sizeof(uint2));
     const size_t o_brec = carve((size_t)G.nblocks * 32 * sizeof(uint32_t));
+    const size_t o_bcount = carve((size_t)G.nblocks * sizeof(uint32_t));
     const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
     const size_t jp = (size_t)((P.Jmax + 15) / 16 * 16);
@@ -310,6 +311,9 @@ void enqueue_tiled(mmg_results *res) {
     X.lookback = reinterpret_cast<uint64_t *>(ws.zero + o_lookback);
     X.ext = reinterpret_cast<uint2 *>(ws.scratch + o_ext);
     X.brec = reinterpret_cast<uint32_t *>(ws.scratch + o_brec);
+    X.bcount = reinterpret_cast<uint32_t *>(ws.scratch + o_bcount);
+    X.ev_total = (uint64_t)t.per_warp * t.total_warps;
+    X.out_off = res->d_off; X.out_val = res->d_val; X.capacity = t.cap;
     X.mcount = reinterpret_cast<uint32_t *>(ws.scratch + o_mcount);
     X.mbase = reinterpret_cast<uint64_t *>(ws.scratch + o_mbase);
     X.segmap = ws.scratch + o_segmap;
@@ -318,11 +322,9 @@ void enqueue_tiled(mmg_results *res) {
     X.ev_per_warp = (uint32_t)t.per_warp;
     X.host_status = res->status_host;             // pinned + mapped: same address on the device (UVA)
 
-    if (res->launches == 0) CU(cudaEventRecord(res->ev[1], stream));      // ev[1] -> ev[2] brackets the filter kernel alone
-    CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
-    if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
-    // A pattern whose previous scan left only a few events per engine block is resolved by the warp-per-block kernel;
-    // should this scan turn out denser the kernel says so and finish_tiled() runs the general one over the same events.
+    // A pattern whose previous scan left only a few events per engine block is resolved inside the filter kernel (one
+    // launch); should this scan turn out denser the kernel says so and finish_tiled() runs the resolve kernel over the
+    // same events.
     {
         const mmg_program *prog = res->rq.prog;
         const uint64_t hint_bytes = prog->last_bytes.load(), hint_events = prog->last_events.load();
@@ -330,10 +332,13 @@ void enqueue_tiled(mmg_results *res) {
         t.sparse = !no_sparse && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
                    (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
     }
-    if (t.sparse) CU(mmg_launch_resolve_sparse(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
-    else CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
+    X.fuse = t.sparse ? 1u : 0u;
+    if (res->launches == 0) CU(cudaEventRecord(res->ev[1], stream));      // ev[1] -> ev[2] brackets the filter kernel alone
+    CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
+    if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
+    if (!t.sparse) CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
     ws.dirty = false;
-    res->launches += t.G.segs_per_block > 1 ? 4 : 2;
+    res->launches += t.sparse ? 1 : (t.G.segs_per_block > 1 ? 4 : 2);
     t.generation = ++ws.generation;
 }
 

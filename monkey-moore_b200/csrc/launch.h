@@ -10,10 +10,9 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
                               cudaStream_t stream);
 cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
                                uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
-// resolve for sparse scans (one warp per engine block); host_status[4] != 0 afterwards: a block was too dense, run mmg_launch_resolve
+// sparse scans: the filter kernels resolve the engine blocks themselves when MmgScratch::fuse is set (no resolve launch);
+// host_status[4] != 0 afterwards: a block was too dense, run mmg_launch_resolve over the same event lists
 bool mmg_sparse_resolve_supported(const MmgGeom &G);
-cudaError_t mmg_launch_resolve_sparse(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
-                                      uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
 cudaError_t mmg_launch_scan(const uint32_t *counts, uint32_t n, uint64_t *bsum, uint64_t *bases, uint64_t *total,
                             cudaStream_t stream);
 cudaError_t mmg_launch_emit(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,

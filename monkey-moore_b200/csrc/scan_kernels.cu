@@ -546,6 +546,176 @@ __device__ __forceinline__ WarpState close_at(const MmgScratch &X, WarpState st,
     return st;
 }
 
+// ------------------------------------------------------------------------------------------
+// Resolve FUSED into the filter kernels, for sparse scans (X.fuse).
+// A pattern like cfg2's leaves a handful of events per 512 KiB engine block.  The general resolve kernel spends a CTA
+// of 128 threads, some ten block-wide barriers and a decoupled look-back on every block whatever it holds, and costs
+// a second launch.  Instead, the warps of the (persistent, fully resident, cooperatively launched) filter grid meet at a
+// grid-wide barrier once the chunks are used up, and then share out the engine blocks: a warp reads the extent words of
+// its block's sub-tiles (one round of loads), the few events behind them (a second round), replays the block's chains
+// through them once -- positions are absolute within the block, so "is this event visited" is a plain lattice test and
+// no per-sub-tile phase is needed -- and leaves the block's matches in a small per-block record.  The last warp to
+// finish turns the per-block counts into output positions, writes the (few) matches in file order, hands the status
+// words to the host and restores the workspace's zero state: the scan is ONE launch, and nothing is fenced or counted
+// per chunk.  A block with more events, or more matches, than the staging area / its record holds raises a flag; the
+// host then runs k_resolve over the same event lists.
+// ------------------------------------------------------------------------------------------
+
+// a filter warp ran out of its private event region: the host grows the buffer and re-runs
+__device__ __forceinline__ bool events_overflowed(const MmgScratch &X) { return *reinterpret_cast<volatile uint64_t *>(X.status) > X.ev_per_warp; }
+
+#define SPARSE_EV_CAP 1024u     // events of one engine block the resolving warp stages (in its idle TMA ring)
+#define SPARSE_REC 32u          // words of a block record: [0] match count, [1..31] byte offsets of the matches in the block
+
+// sm: >= SPARSE_EV_CAP words of this warp's shared memory
+template <int W>
+__device__ __noinline__ void sparse_block(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t bi, uint32_t *sm,
+                                          int lane) {
+    uint32_t m = 0;                                       // matches of this block
+    const uint32_t t0 = bi * G.spb;
+    const uint32_t nsb = min(G.spb, G.nsub - t0);         // sub-tiles of this block (<= 128)
+    // round 1: the extent words of the lane's four sub-tiles
+    uint2 ex[4];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t j = 4u * (uint32_t)lane + (uint32_t)k;
+        ex[k] = j < nsb ? __ldcg(X.ext + t0 + j) : make_uint2(0u, 0u);
+        if ((uint64_t)ex[k].x + ex[k].y > X.ev_total) ex[k].y = SPARSE_EV_CAP + 1u;      // a warp overflowed its event region: the host re-runs
+        mine += ex[k].y;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t n = __shfl_sync(FULL, incl, 31);
+    bool dense = n > SPARSE_EV_CAP;
+    if (!dense && n != 0) {
+        // round 2: the events, as  byte offset in the block [18:0] | advance [26:19] | match [27]
+        uint32_t at = incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t base = (4u * (uint32_t)lane + (uint32_t)k) << MMG_SUBTILE_SHIFT;
+            for (uint32_t j = 0; j < ex[k].y; j++) {
+                const uint32_t w = __ldcg(X.ev + ex[k].x + j);
+                sm[at++] = (base + MMG_EV_OFF(w)) | (MMG_EV_JUMP(w) << 19) | ((w & MMG_EV_MATCH) ? (1u << 27) : 0u);
+            }
+        }
+        __syncwarp();
+        // replay, every lane the same: the chains of the block's alignment classes start at its first element
+        const uint32_t J0 = P.J0;
+        const uint32_t magic = 0xFFFFFFFFu / J0 + 1u;     // floor(2^32 / J0) + 1 (2^32 / J0 for powers of two): exact quotients below 2^19
+        uint32_t xc[2] = {0u, 0u};
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t e = sm[i];
+            const uint32_t bo = e & 0x7FFFFu;
+            const uint32_t c = (W == 2) ? (bo & 1u) : 0u;
+            const uint32_t q = bo / W, x = xc[c];
+            if (x <= q) {
+                const uint32_t d = q - x;
+                if (J0 == 1u || d - __umulhi(d, magic) * J0 == 0u) {
+                    xc[c] = q + ((e >> 19) & 0xFFu);
+                    if (e & (1u << 27)) {
+                        __syncwarp();                     // every lane has read entry i
+                        if (lane == 0) sm[m] = bo;        // m <= i: never ahead of the read position
+                        m++;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        dense = m >= SPARSE_REC;
+    }
+    if (dense) {
+        if (lane == 0) atomicOr(X.ticket + 2, 1u);        // not sparse after all: the host falls back to k_resolve
+        m = 0;
+    }
+    uint32_t *rec = X.brec + (size_t)bi * SPARSE_REC;
+    if (lane == 0) { rec[0] = m; X.bcount[bi] = m; }
+    if (lane < (int)m) rec[1 + lane] = sm[lane];
+    __syncwarp();
+}
+
+// The last warp of the grid: output positions (prefix over the block counts), emission, status words, zero state.
+template <int W, bool BE>
+__device__ __noinline__ void sparse_finish(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lane) {
+    const uint32_t nb = G.nblocks;
+    const uint32_t per = (nb + 31u) / 32u;                // blocks per lane, contiguous
+    const uint32_t b_lo = min(nb, (uint32_t)lane * per), b_hi = min(nb, b_lo + per);
+    uint64_t mine = 0;
+    for (uint32_t b = b_lo; b < b_hi; b++) mine += __ldcg(X.bcount + b);
+    uint64_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint64_t total = __shfl_sync(FULL, incl, 31);
+    if (mine != 0) {
+        const uint32_t o0 = (uint32_t)P.first_lit * W;
+        const bool has1 = P.opp_idx >= 0;
+        const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
+        uint64_t at = incl - mine;
+        for (uint32_t b = b_lo; b < b_hi; b++) {
+            const uint32_t *rec = X.brec + (size_t)b * SPARSE_REC;
+            const uint32_t cnt = __ldcg(rec);
+            const uint64_t blk_off = (uint64_t)b * G.B;
+            for (uint32_t i = 0; i < cnt && at < X.capacity; i++, at++) {
+                const uint64_t sb = blk_off + __ldcg(rec + 1 + i);
+                uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
+                if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
+                X.out_off[at] = (G.base_offset + sb) >> G.report_shift;
+                X.out_val[at] = v;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence();
+    if (lane < 2) X.host_status[lane] = reinterpret_cast<volatile uint64_t *>(X.status)[lane];
+    if (lane == 2) X.host_status[2] = total;
+    if (lane == 3) X.host_status[3] = 0;
+    if (lane == 4) X.host_status[4] = reinterpret_cast<volatile uint32_t *>(X.ticket)[2];
+    // (no system fence: the status slot is read by the host after the kernel has completed)
+    __syncwarp();
+    if (lane < 4) X.status[lane] = 0;
+    if (lane < 4) X.ticket[lane] = 0;
+}
+
+// End of a filter CTA in a fused scan.  ticket[1] counts the CTAs whose warps have all used up the chunks (grid barrier:
+// the grid is persistent and launched cooperatively, so every CTA is resident; ONE thread per CTA polls, with a
+// back-off -- thousands of pollers on one word saturate its L2 slice and stall the bulk copies that still run),
+// ticket[3] the CTAs that have resolved their blocks.
+__shared__ uint32_t g_fuse_last;
+
+template <int W, bool BE>
+__device__ __forceinline__ void fused_tail(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t *sm, int lane) {
+    const uint32_t wpc = blockDim.x >> 5;
+    const uint32_t nwarps = gridDim.x * wpc;
+    const uint32_t me = blockIdx.x * wpc + (threadIdx.x >> 5);
+    __threadfence();                                      // this warp's extent words and events, before its CTA arrives
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(X.ticket + 1, 1u);
+        volatile uint32_t *arrived = X.ticket + 1;
+        uint32_t ns = 100;
+        while (*arrived < gridDim.x) { __nanosleep(ns); ns = min(ns * 2u, 800u); }
+    }
+    __syncthreads();
+    __threadfence();
+    if (!events_overflowed(X))                            // (otherwise the lists are incomplete and the host re-runs the scan)
+        for (uint32_t b = me; b < G.nblocks; b += nwarps) sparse_block<W>(P, G, X, b, sm, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) g_fuse_last = atomicAdd(X.ticket + 3, 1u) + 1u == gridDim.x ? 1u : 0u;
+    __syncthreads();
+    if (g_fuse_last && threadIdx.x < 32) {
+        __threadfence();
+        sparse_finish<W, BE>(P, G, X, lane);
+    }
+}
+
 template <int W, int LB, bool BE, int NK>
 __global__ void __launch_bounds__(MMG_FILTER_WARPS * 32, MMG_FILTER_MIN_CTAS)
 k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X) {
@@ -707,6 +877,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
         atomicAdd((unsigned long long *)&X.status[1], (unsigned long long)(st.cursor - reg_lo));
     }
+    if (X.fuse) fused_tail<W, BE>(P, G, X, reinterpret_cast<uint32_t *>(ring), lane);
 }
 
 
@@ -917,10 +1088,9 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
         atomicAdd((unsigned long long *)&X.status[1], (unsigned long long)(st.cursor - reg_lo));
     }
+    if (X.fuse) fused_tail<1, false>(P, G, X, reinterpret_cast<uint32_t *>(ring), lane);
 }
 
-// a filter warp ran out of its private event region: the host grows the buffer and re-runs
-__device__ __forceinline__ bool events_overflowed(const MmgScratch &X) { return X.status[0] > X.ev_per_warp; }
 
 // ------------------------------------------------------------------------------------------
 // K2: resolve -- everything after the filter in ONE kernel, one warp per engine block
@@ -1297,158 +1467,13 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     if (s_last) {
         __threadfence();
         if (tid < 4) X.host_status[tid] = reinterpret_cast<volatile uint64_t *>(X.status)[tid];
-        if (tid == 4) X.host_status[4] = 0;                       // (k_resolve_sparse reports "too dense" here)
+        if (tid == 4) X.host_status[4] = 0;                       // (the fused sparse resolve reports "too dense" here)
         __threadfence_system();
         __syncthreads();
         if (tid < 4) X.status[tid] = 0;
         if (tid < 2) X.ticket[tid] = 0;
         for (uint32_t i = tid; i < G.nseg; i += RESOLVE_THREADS) X.lookback[i] = 0;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2s: resolve for SPARSE scans -- one WARP per engine block, direct replay, no maps, no look-back.
-// A pattern like cfg2's leaves a handful of events per 512 KiB block.  k_resolve spends a CTA of 128 threads and some
-// ten block-wide barriers on each block whatever it holds, and its decoupled look-back keeps a thousand nearly idle
-// CTAs spinning on each other.  Here a warp reads the extent words of its block's sub-tiles (one round of loads), the
-// few events behind them (a second round), replays the block's chains through them once -- positions are absolute
-// within the block, so "is this event visited" is a plain lattice test and no per-sub-tile phase is needed -- and leaves
-// the block's matches in a small per-block record.  The LAST CTA to finish turns the per-block counts into output
-// positions and writes the (few) matches in file order.  A block with more events, or more matches, than its record
-// holds raises a flag; the host then runs k_resolve over the same event lists.
-// ------------------------------------------------------------------------------------------
-
-#define SPARSE_WARPS 8
-#define SPARSE_EV_CAP 1024u
-#define SPARSE_REC 32u          // words of a block record: [0] match count, [1..31] byte offsets of the matches in the block
-
-template <int W, bool BE>
-__global__ void __launch_bounds__(SPARSE_WARPS * 32)
-k_resolve_sparse(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
-                 uint64_t *out_off, uint32_t *out_val, uint64_t capacity) {
-    __shared__ uint32_t s_ev[SPARSE_WARPS][SPARSE_EV_CAP];
-    __shared__ uint32_t s_last;
-    __shared__ uint64_t s_scan[SPARSE_WARPS];
-    __shared__ uint64_t s_carry;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *sm = s_ev[wid];
-    const bool bad = events_overflowed(X);
-    const uint32_t bi = blockIdx.x * SPARSE_WARPS + (uint32_t)wid;
-
-    if (bi < G.nblocks) {
-        uint32_t m = 0;                                       // matches of this block
-        const uint32_t t0 = bi * G.spb;
-        const uint32_t nsb = bad ? 0u : min(G.spb, G.nsub - t0);          // sub-tiles of this block (<= 128)
-        // round 1: the extent words of the lane's four sub-tiles
-        uint2 ex[4];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t j = 4u * (uint32_t)lane + (uint32_t)k;
-            ex[k] = j < nsb ? X.ext[t0 + j] : make_uint2(0u, 0u);
-            mine += ex[k].y;
-        }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t n = __shfl_sync(FULL, incl, 31);
-        bool dense = n > SPARSE_EV_CAP;
-        if (!dense && n != 0) {
-            // round 2: the events, as  byte offset in the block [18:0] | advance [26:19] | match [27]
-            uint32_t at = incl - mine;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t base = (4u * (uint32_t)lane + (uint32_t)k) << MMG_SUBTILE_SHIFT;
-                for (uint32_t j = 0; j < ex[k].y; j++) {
-                    const uint32_t w = X.ev[ex[k].x + j];
-                    sm[at++] = (base + MMG_EV_OFF(w)) | (MMG_EV_JUMP(w) << 19) | ((w & MMG_EV_MATCH) ? (1u << 27) : 0u);
-                }
-            }
-            __syncwarp();
-            // replay, every lane the same: the chains of the block's alignment classes start at its first element
-            const uint32_t J0 = P.J0;
-            const uint32_t magic = 0xFFFFFFFFu / J0 + 1u;     // floor(2^32 / J0) + 1 (2^32 / J0 for powers of two): exact quotients below 2^19
-            uint32_t xc[2] = {0u, 0u};
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t e = sm[i];
-                const uint32_t bo = e & 0x7FFFFu;
-                const uint32_t c = (W == 2) ? (bo & 1u) : 0u;
-                const uint32_t q = bo / W, x = xc[c];
-                if (x <= q) {
-                    const uint32_t d = q - x;
-                    if (J0 == 1u || d - __umulhi(d, magic) * J0 == 0u) {
-                        xc[c] = q + ((e >> 19) & 0xFFu);
-                        if (e & (1u << 27)) {
-                            __syncwarp();                     // every lane has read entry i
-                            if (lane == 0) sm[m] = bo;        // m <= i: never ahead of the read position
-                            m++;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            dense = m >= SPARSE_REC;
-        }
-        if (dense) {
-            if (lane == 0) atomicOr(X.ticket + 2, 1u);        // not sparse after all: the host falls back to k_resolve
-            m = 0;
-        }
-        uint32_t *rec = X.brec + (size_t)bi * SPARSE_REC;
-        if (lane == 0) rec[0] = m;
-        if (lane < (int)m) rec[1 + lane] = sm[lane];
-    }
-
-    // ---- the last CTA to finish: output positions (prefix over the block counts), emission, status, zero state
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(X.ticket + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const uint32_t o0 = (uint32_t)P.first_lit * W;
-    const bool has1 = P.opp_idx >= 0;
-    const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
-    const volatile uint32_t *brec = X.brec;
-    for (uint32_t b0 = 0; b0 < G.nblocks; b0 += SPARSE_WARPS * 32) {
-        const uint32_t b = b0 + threadIdx.x;
-        const uint32_t cnt = b < G.nblocks ? brec[(size_t)b * SPARSE_REC] : 0u;
-        uint64_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_scan[wid] = incl;
-        __syncthreads();
-        uint64_t wbase = s_carry, tile = 0;
-        for (int i = 0; i < SPARSE_WARPS; i++) { if (i < wid) wbase += s_scan[i]; tile += s_scan[i]; }
-        uint64_t at = wbase + incl - cnt;
-        const uint64_t blk_off = (uint64_t)b * G.B;
-        for (uint32_t i = 0; i < cnt && at < capacity; i++, at++) {
-            const uint64_t sb = blk_off + brec[(size_t)b * SPARSE_REC + 1 + i];
-            uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
-            if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
-            out_off[at] = (G.base_offset + sb) >> G.report_shift;
-            out_val[at] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += tile;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) X.status[2] = s_carry;
-    __syncthreads();
-    __threadfence();
-    if (threadIdx.x < 4) X.host_status[threadIdx.x] = reinterpret_cast<volatile uint64_t *>(X.status)[threadIdx.x];
-    if (threadIdx.x == 4) X.host_status[4] = reinterpret_cast<volatile uint32_t *>(X.ticket)[2];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < 4) X.status[threadIdx.x] = 0;
-    if (threadIdx.x < 3) X.ticket[threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1724,6 +1749,8 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
     const void *fn = filter_kernel(P.W, lag_bytes, G.big_endian != 0, P.nkeys);
     if (!fn) return cudaErrorInvalidValue;
     void *args[] = {(void *)&P, (void *)&G, (void *)&X};
+    // a fused scan ends in a grid-wide barrier: cooperative launch guarantees that the whole grid is resident
+    if (X.fuse) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, filter_smem(P.W, lag_bytes), stream);
     return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, filter_smem(P.W, lag_bytes), stream);
 }
 
@@ -1750,15 +1777,6 @@ cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgS
 }
 
 bool mmg_sparse_resolve_supported(const MmgGeom &G) { return G.segs_per_block == 1 && G.spb <= 128; }
-
-cudaError_t mmg_launch_resolve_sparse(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
-                                      uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
-    const unsigned grid = (G.nblocks + SPARSE_WARPS - 1) / SPARSE_WARPS;
-    if (P.W == 1) k_resolve_sparse<1, false><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
-    else if (G.big_endian) k_resolve_sparse<2, true><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
-    else k_resolve_sparse<2, false><<<grid, SPARSE_WARPS * 32, 0, stream>>>(P, G, X, out_off, out_val, capacity);
-    return cudaGetLastError();
-}
 
 // exclusive scan of n u32 counts into u64 bases; bsum must hold ceil(n/1024) entries; *total receives the sum
 cudaError_t mmg_launch_scan(const uint32_t *counts, uint32_t n, uint64_t *bsum, uint64_t *bases, uint64_t *total,

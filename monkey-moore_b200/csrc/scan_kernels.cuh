@@ -62,14 +62,22 @@ struct MmgScratch {
     uint2 *ext;            // [nsub] {first event, number of events} of the sub-tile, written for EVERY sub-tile by the filter
     uint32_t *mcount;      // [nsub] visited matches (valid where the sub-tile has events)
     uint64_t *mbase;       // [nsub] position of the sub-tile's first match in the output (ditto)
-    uint32_t *brec;        // [nblocks][32] k_resolve_sparse: per-block record {match count, byte offsets of the matches}
+    // ---- fused resolve of sparse scans (scan_kernels.cu, "Resolve FUSED into the filter kernels")
+    uint32_t fuse;         // != 0: the filter kernel resolves the engine blocks itself
+    uint32_t *brec;        // [nblocks][32] per-block record {match count, byte offsets of the matches}
+    uint32_t *bcount;      // [nblocks] match count of the block (compact copy for the final prefix)
+    uint64_t ev_total;     // entries of `ev`
+    uint64_t *out_off;     // the scan's result buffers (the last warp of the grid writes the matches)
+    uint32_t *out_val;
+    uint64_t capacity;
     // Zero state: all zero when a scan starts.  The last CTA of the resolve kernel to finish copies `status` to the
     // host's pinned slot and zeroes it all again, so a workspace serves scan after scan without a memset.
     uint64_t *status;      // [0] events needed by the fullest warp region (overflow check) [1] total events
                            // [2] total matches [3] next chunk (dynamic scheduling)
     uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts
     uint32_t *ticket;      // [0] block ticket of the resolve kernel  [1] CTAs of the resolve kernel that are done
-                           // [2] k_resolve_sparse: a block held more events than it can stage
+                           // [2] fused resolve: a block held more events / matches than it can stage
+                           // [3] fused resolve: warps that have resolved their blocks ([1]: warps that left the filter loop)
     uint64_t *host_status; // pinned, device-visible: receives status[0..3] (+ [4] = ticket[2]) when the resolve kernel ends
     uint8_t *segmap;       // [nseg][2][jp] entry phase -> exit phase of a whole segment (only when segs_per_block > 1)
     uint8_t *segphase;     // [nseg][2] entry phase of the segment
