@@ -172,6 +172,10 @@ void mmg_gathered_free(mmg_gathered *g);
  * such a buffer so that the H2D copy runs at PCIe speed).  NULL when allocation fails / no device. */
 void *mmg_host_alloc(uint64_t nbytes);
 void mmg_host_free(void *p);
+/* memcpy split over the library's pool of host threads (file pages / pageable memory -> staging memory at more than one
+ * core's copy bandwidth).  Host pointers passed to the scan calls with MMG_MEM_HOST need no preparation: page-locked
+ * ones are copied directly, pageable ones of 4 MiB and more go through the library's own pinned staging ring. */
+int mmg_host_copy(void *dst, const void *src, uint64_t nbytes);
 
 /* Stream selection for the calling thread: use_it != 0 makes every later scan of this thread run on
  * `cuda_stream` (a cudaStream_t; NULL is the legacy default stream), so a caller can bracket scans with

