@@ -399,7 +399,7 @@ void enqueue_tiled(mmg_results *res) {
     auto carve = [&](size_t bytes) { size_t at = off; off = (off + bytes + 255) & ~(size_t)255; return at; };
     // zero state
     const size_t o_status = carve(4 * sizeof(uint64_t));
-    const size_t o_ticket = carve(4 * sizeof(uint32_t));
+    const size_t o_ticket = carve(8 * sizeof(uint32_t));
     const size_t o_lookback = carve((size_t)G.nseg * sizeof(uint64_t));
     const size_t zero_need = off;
     off = 0;

@@ -638,41 +638,34 @@ __device__ __noinline__ void sparse_block(const MmgProgram &P, const MmgGeom &G,
     __syncwarp();
 }
 
-// The last warp of the grid: output positions (prefix over the block counts), emission, status words, zero state.
+// Emission of one resolved block: its position in the output is the sum of the counts of the blocks before it (a warp
+// reads them coalesced: a few KB from L2), then one lane per match.
 template <int W, bool BE>
-__device__ __noinline__ void sparse_finish(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, int lane) {
-    const uint32_t nb = G.nblocks;
-    const uint32_t per = (nb + 31u) / 32u;                // blocks per lane, contiguous
-    const uint32_t b_lo = min(nb, (uint32_t)lane * per), b_hi = min(nb, b_lo + per);
-    uint64_t mine = 0;
-    for (uint32_t b = b_lo; b < b_hi; b++) mine += __ldcg(X.bcount + b);
-    uint64_t incl = mine;
+__device__ __forceinline__ void sparse_emit_block(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint32_t b, int lane) {
+    const uint32_t cnt = __ldcg(X.bcount + b);
+    if (cnt == 0) return;
+    uint64_t before = 0;
+    for (uint32_t j = lane; j < b; j += 32) before += __ldcg(X.bcount + j);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const uint64_t total = __shfl_sync(FULL, incl, 31);
-    if (mine != 0) {
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULL, before, o);
+    if ((uint32_t)lane < cnt && before + lane < X.capacity) {
         const uint32_t o0 = (uint32_t)P.first_lit * W;
         const bool has1 = P.opp_idx >= 0;
         const uint32_t o1 = has1 ? (uint32_t)P.opp_idx * W : 0u;
-        uint64_t at = incl - mine;
-        for (uint32_t b = b_lo; b < b_hi; b++) {
-            const uint32_t *rec = X.brec + (size_t)b * SPARSE_REC;
-            const uint32_t cnt = __ldcg(rec);
-            const uint64_t blk_off = (uint64_t)b * G.B;
-            for (uint32_t i = 0; i < cnt && at < X.capacity; i++, at++) {
-                const uint64_t sb = blk_off + __ldcg(rec + 1 + i);
-                uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
-                if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
-                X.out_off[at] = (G.base_offset + sb) >> G.report_shift;
-                X.out_val[at] = v;
-            }
-        }
+        const uint64_t sb = (uint64_t)b * G.B + __ldcg(X.brec + (size_t)b * SPARSE_REC + 1 + lane);
+        uint32_t v = ld_elem<W, BE>(G.data + sb + o0);
+        if (has1) v |= ld_elem<W, BE>(G.data + sb + o1) << 16;
+        X.out_off[before + lane] = (G.base_offset + sb) >> G.report_shift;
+        X.out_val[before + lane] = v;
     }
-    __syncwarp();
-    __threadfence();
+}
+
+// The last CTA of the grid (its first warp): total, status words for the host, zero state of the workspace.
+__device__ __noinline__ void sparse_last(const MmgGeom &G, const MmgScratch &X, int lane) {
+    uint64_t total = 0;
+    for (uint32_t j = lane; j < G.nblocks; j += 32) total += __ldcg(X.bcount + j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
     if (lane < 2) X.host_status[lane] = reinterpret_cast<volatile uint64_t *>(X.status)[lane];
     if (lane == 2) X.host_status[2] = total;
     if (lane == 3) X.host_status[3] = 0;
@@ -680,13 +673,28 @@ __device__ __noinline__ void sparse_finish(const MmgProgram &P, const MmgGeom &G
     // (no system fence: the status slot is read by the host after the kernel has completed)
     __syncwarp();
     if (lane < 4) X.status[lane] = 0;
-    if (lane < 4) X.ticket[lane] = 0;
+    if (lane < 8) X.ticket[lane] = 0;
 }
 
-// End of a filter CTA in a fused scan.  ticket[1] counts the CTAs whose warps have all used up the chunks (grid barrier:
-// the grid is persistent and launched cooperatively, so every CTA is resident; ONE thread per CTA polls, with a
-// back-off -- thousands of pollers on one word saturate its L2 slice and stall the bulk copies that still run),
-// ticket[3] the CTAs that have resolved their blocks.
+// CTA-level arrival at a grid-wide barrier: the grid is persistent and launched cooperatively, so every CTA is resident.
+// ONE thread per CTA polls, with a back-off -- thousands of pollers on one word saturate its L2 slice and stall the bulk
+// copies of the CTAs that still filter.
+__device__ __forceinline__ void grid_barrier(uint32_t *counter) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        volatile uint32_t *arrived = counter;
+        uint32_t ns = 100;
+        while (*arrived < gridDim.x) { __nanosleep(ns); ns = min(ns * 2u, 400u); }
+    }
+    __syncthreads();
+    __threadfence();
+}
+
+// End of a filter CTA in a fused scan: barrier (every chunk is filtered) -- the warps share out the engine blocks and
+// resolve them -- barrier (every block's match count is known) -- the warps write their blocks' matches -- the last CTA
+// to get here reports.  ticket[1], [3]: the barriers; [4]: CTAs that are done.
 __shared__ uint32_t g_fuse_last;
 
 template <int W, bool BE>
@@ -694,25 +702,22 @@ __device__ __forceinline__ void fused_tail(const MmgProgram &P, const MmgGeom &G
     const uint32_t wpc = blockDim.x >> 5;
     const uint32_t nwarps = gridDim.x * wpc;
     const uint32_t me = blockIdx.x * wpc + (threadIdx.x >> 5);
-    __threadfence();                                      // this warp's extent words and events, before its CTA arrives
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(X.ticket + 1, 1u);
-        volatile uint32_t *arrived = X.ticket + 1;
-        uint32_t ns = 100;
-        while (*arrived < gridDim.x) { __nanosleep(ns); ns = min(ns * 2u, 800u); }
+    grid_barrier(X.ticket + 1);
+    const bool ok = !events_overflowed(X);                // (otherwise the lists are incomplete and the host re-runs the scan)
+    for (uint32_t b = me; b < G.nblocks; b += nwarps) {
+        if (ok) sparse_block<W>(P, G, X, b, sm, lane);
+        else if (lane == 0) X.bcount[b] = 0;
     }
-    __syncthreads();
+    grid_barrier(X.ticket + 3);
+    if (ok)
+        for (uint32_t b = me; b < G.nblocks; b += nwarps) sparse_emit_block<W, BE>(P, G, X, b, lane);
     __threadfence();
-    if (!events_overflowed(X))                            // (otherwise the lists are incomplete and the host re-runs the scan)
-        for (uint32_t b = me; b < G.nblocks; b += nwarps) sparse_block<W>(P, G, X, b, sm, lane);
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) g_fuse_last = atomicAdd(X.ticket + 3, 1u) + 1u == gridDim.x ? 1u : 0u;
+    if (threadIdx.x == 0) g_fuse_last = atomicAdd(X.ticket + 4, 1u) + 1u == gridDim.x ? 1u : 0u;
     __syncthreads();
     if (g_fuse_last && threadIdx.x < 32) {
         __threadfence();
-        sparse_finish<W, BE>(P, G, X, lane);
+        sparse_last(G, X, lane);
     }
 }
 

@@ -77,7 +77,8 @@ struct MmgScratch {
     uint64_t *lookback;    // [nblocks] decoupled look-back words of the per-block match counts
     uint32_t *ticket;      // [0] block ticket of the resolve kernel  [1] CTAs of the resolve kernel that are done
                            // [2] fused resolve: a block held more events / matches than it can stage
-                           // [3] fused resolve: warps that have resolved their blocks ([1]: warps that left the filter loop)
+                           // fused resolve: [1], [3] grid barriers (CTAs that left the filter loop / resolved their blocks),
+                           // [4] CTAs that are done
     uint64_t *host_status; // pinned, device-visible: receives status[0..3] (+ [4] = ticket[2]) when the resolve kernel ends
     uint8_t *segmap;       // [nseg][2][jp] entry phase -> exit phase of a whole segment (only when segs_per_block > 1)
     uint8_t *segphase;     // [nseg][2] entry phase of the segment
