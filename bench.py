@@ -291,6 +291,7 @@ def measure(ctx, args, w, steps, warmup, headline):
                 for prog, s in zip(progs, w.searches)]
 
     gather_ms = [0.0, 0]
+    last_gather = [None]
 
     def complete_step(held, keep=None):
         """host side of a step: statistics, the gather (N > 1), release.  keep: list that receives what rank 0 got."""
@@ -305,8 +306,12 @@ def measure(ctx, args, w, steps, warmup, headline):
             g = comm.gather(held, lazy=True)       # ONE grouped NCCL op per step, on the communicator's own stream
             if keep is not None:
                 keep.append(g)
-            elif g is not None:
-                g.close()
+            else:
+                # rank 0 reads the headers of this gather when the NEXT one starts (or in comm.wait()): dropping the
+                # previous object here costs nothing, dropping this one now would wait for the packed buffers
+                old, last_gather[0] = last_gather[0], g
+                if old is not None:
+                    old.close()
         for r in held:
             r.close()
         return launches, filt_ms, filt_bytes, scan_ms
@@ -330,17 +335,19 @@ def measure(ctx, args, w, steps, warmup, headline):
     barrier()
     e0.record(stream)
     t0 = time.perf_counter()
-    # software pipeline over the steps: step k+1 is enqueued before the host collects step k (counts, statistics,
-    # gather), so the device never waits for the host between steps; every step is complete before the clock stops
-    prev = None
+    # software pipeline over the steps: the next step(s) are enqueued before the host collects step k (counts,
+    # statistics, gather), so the device never waits for the host between steps; every step is complete before the
+    # clock stops
+    inflight = []
+    depth = 2 if world > 1 else 1          # N > 1: the gather of step k travels while steps k+1 and k+2 scan
     for _ in range(steps):
-        cur = enqueue_step()
-        if prev is not None:
-            a = complete_step(prev)
+        inflight.append(enqueue_step())
+        if len(inflight) > depth:
+            a = complete_step(inflight.pop(0))
             launches += a[0]; filt_ms += a[1]; filt_bytes += a[2]; scan_ms += a[3]
-        prev = cur
-    a = complete_step(prev)
-    launches += a[0]; filt_ms += a[1]; filt_bytes += a[2]; scan_ms += a[3]
+    while inflight:
+        a = complete_step(inflight.pop(0))
+        launches += a[0]; filt_ms += a[1]; filt_bytes += a[2]; scan_ms += a[3]
     e1.record(stream)
     if world > 1:
         gather_ms[0] = comm.wait()             # the last step's lists have landed on rank 0 / left this rank

@@ -150,9 +150,10 @@ int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
  *   mmg_comm_create    : collective over all ranks; capacity = entries of the fixed packed buffer.
  *   mmg_comm_gather    : collective; the `nlists` lists of one step (same nlists on every rank) go to
  *                        rank 0 in ONE grouped NCCL operation (+ point-to-point sends of whatever exceeds
- *                        the packed capacity; rank 0 posts the matching receives before its call returns,
- *                        so no send stays unmatched behind the call).  *out is non-NULL on rank 0 only.
- *                        The lists may be freed right after the call on every rank.
+ *                        the packed capacity; rank 0 posts the matching receives when the gathered object is
+ *                        first used, at the latest at its next mmg_comm_gather / mmg_comm_wait call -- a send
+ *                        that waits blocks only the gather stream).  The call only enqueues work.  *out is
+ *                        non-NULL on rank 0 only.  The lists may be freed right after the call on every rank.
  *   mmg_comm_wait      : blocks until this rank's part of every gather so far has executed; *ms_last
  *                        (may be NULL) = device time of the last gather on this rank's gather stream.
  *   mmg_gathered_pieces: device-resident pieces (rank order == file order) of one gathered list. */

@@ -11,9 +11,12 @@
 //      buffers to rank 0;
 //   2. a rank whose lists do not fit enqueues point-to-point sends of the remainder right behind
 //      the packed send;
-//   3. rank 0 reads the gathered headers INSIDE the call (one small D2H + event wait) and posts the
-//      matching receives before it returns -- a pending send never outlives the call that caused it,
-//      so no later collective (of this or any other communicator) can queue behind an unmatched send.
+//   3. rank 0 learns from the gathered headers what did not fit and posts the matching receives.  It
+//      does so LAZILY -- when the gathered object is first used, and at the latest at the start of
+//      the next gather (so receives and sends of consecutive gathers pair up in order) or in
+//      mmg_comm_wait -- which keeps the host of rank 0 off the critical path of a pipelined scan
+//      loop.  A send that waits for its receive blocks nothing but the dedicated gather stream:
+//      the scan streams and the collectives of other communicators run beside it.
 //
 // Everything runs on a dedicated, process-wide gather stream of the device: the scan streams never wait for NCCL, and a
 // list that is still being read by a send is released in gather-stream order (the results object is
@@ -102,6 +105,7 @@ struct mmg_comm {
     uint64_t *recv_off = nullptr;   // rank 0: world * cap
     uint32_t *recv_val = nullptr;
     uint64_t *hdr_host = nullptr;   // pinned, rank 0: the headers of all ranks (HDR entries per rank)
+    mmg_gathered *inflight = nullptr;   // rank 0: the gather whose headers have not been read yet
 };
 
 struct mmg_gathered {
@@ -114,12 +118,67 @@ struct mmg_gathered {
     cudaStream_t stream = nullptr;
     cudaEvent_t landed = nullptr;                 // every piece has arrived on rank 0
     bool waited = false;
+    // deferred part (rank 0): the other ranks' headers are read and their overflow received on first use
+    bool pending = false;
+    mmg_comm *comm = nullptr;
+    int error = MMG_OK;
 };
 
 namespace {
 
+// rank 0: read the gathered headers of ranks 1.., build their piece lists, receive what did not fit
+int complete_gather(mmg_gathered *g) {
+    if (!g->pending) return g->error;
+    g->pending = false;
+    mmg_comm *c = g->comm;
+    if (c->inflight == g) c->inflight = nullptr;
+    cudaStream_t stream = g->stream;
+    const int nlists = g->nlists;
+    const uint64_t room = c->cap - (uint64_t)nlists;
+    auto bail = [&](int code) { g->error = code; return code; };
+    if (cudaEventSynchronize(c->hdr_ready) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "waiting for the gathered headers failed"));
+    const uint64_t *all = c->hdr_host;
+    struct Spill { int rank; uint64_t *off; uint32_t *val; uint64_t n; };
+    std::vector<Spill> spills;
+    for (int r = 1; r < c->world; r++) {
+        uint64_t pos = nlists, used_r = 0;
+        for (int k = 0; k < nlists; k++) {
+            const uint64_t n = all[(size_t)r * HDR + k];
+            const uint64_t f = std::min<uint64_t>(n, room - used_r);
+            g->counts[k] += n;
+            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
+            pos += f; used_r += f;
+            if (f < n) {
+                const uint64_t rest = n - f;
+                uint64_t *so = nullptr; uint32_t *sv = nullptr;
+                if (cudaMallocAsync((void **)&so, rest * sizeof(uint64_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
+                g->owned.push_back(so);
+                if (cudaMallocAsync((void **)&sv, rest * sizeof(uint32_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
+                g->owned.push_back(sv);
+                spills.push_back({r, so, sv, rest});
+                g->pieces[k].push_back({so, sv, rest});
+            }
+        }
+    }
+    if (!spills.empty()) {
+        // same order per peer as the sends (list by list, offsets then values); one group so that all peers stream at once
+        if (nccl().GroupStart() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupStart failed"));
+        for (const Spill &sp : spills) {
+            if (nccl().Recv(sp.off, sp.n, ncclUint64, sp.rank, c->comm, stream) != ncclSuccess ||
+                nccl().Recv(sp.val, sp.n, ncclUint32, sp.rank, c->comm, stream) != ncclSuccess)
+                return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
+        }
+        if (nccl().GroupEnd() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupEnd failed"));
+    }
+    if (cudaEventRecord(c->t1, stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
+    c->timed = true;
+    if (cudaEventRecord(g->landed, stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
+    return MMG_OK;
+}
+
 void destroy_comm(mmg_comm *c) {
     if (!c) return;
+    if (c->inflight) complete_gather(c->inflight);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
     cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
@@ -131,6 +190,7 @@ void destroy_comm(mmg_comm *c) {
 }
 
 int wait_landed(mmg_gathered *g) {
+    if (int rc = complete_gather(g); rc != MMG_OK) return rc;
     if (g->waited) return MMG_OK;
     if (cudaEventSynchronize(g->landed) != cudaSuccess) return err(MMG_ERR_CUDA, "waiting for the gathered lists failed");
     g->waited = true;
@@ -184,11 +244,15 @@ void mmg_comm_destroy(mmg_comm *c) { destroy_comm(c); }
 
 // Gathers `nlists` result lists (the searches of one step) of every rank to rank 0.
 // On rank 0 *out receives the gathered lists (rank order == ascending file offsets); elsewhere NULL.
-// Blocks the HOST of rank 0 until the packed buffers of all ranks have arrived (their headers size the
-// receives of whatever did not fit); the other ranks only enqueue.  The scan streams are never involved.
+// Every rank only ENQUEUES work on the gather stream (rank 0 first completes its previous gather, whose headers have
+// long arrived by then); rank 0 reads the other ranks' headers and posts the receives of whatever did not fit when the
+// gathered object is first used.  The scan streams are never involved.
 int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out) {
     if (!c || !lists || nlists <= 0 || nlists > HDR - 4 || !out) return err(MMG_ERR_ARG, "bad gather arguments");
     *out = nullptr;
+    // the previous gather's headers live in the buffer this one reuses, and its overflow receives must be posted before
+    // this gather's receives (sends and receives of a pair of ranks match in order)
+    if (c->inflight) complete_gather(c->inflight);
     cudaStream_t stream = c->stream;
     const uint64_t room = c->cap - (uint64_t)nlists;
     std::vector<mmg_results_view> v(nlists);
@@ -247,28 +311,22 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
         return MMG_OK;
     }
 
-    // ---- rank 0: everybody's headers, then the receives of what did not fit
-    CUC(cudaMemcpy2DAsync(c->hdr_host, HDR * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t),
-                          (size_t)nlists * sizeof(uint64_t), c->world, cudaMemcpyDeviceToHost, stream));
-    CUC(cudaEventRecord(c->hdr_ready, stream));
-    CUC(cudaEventSynchronize(c->hdr_ready));
+    // ---- rank 0: its own lists are complete here (what did not fit is copied now, while the lists are known to be alive);
+    // the other ranks' headers travel to the host and are read when the gathered object is first used
     mmg_gathered *g = new mmg_gathered();
     g->nlists = nlists;
     g->counts.assign(nlists, 0);
     g->pieces.resize(nlists);
     g->stream = stream;
+    g->comm = c;
     auto bail = [&](int code) { mmg_gathered_free(g); return code; };
-    const uint64_t *all = c->hdr_host;
-    struct Spill { int rank; uint64_t *off; uint32_t *val; uint64_t n; };
-    std::vector<Spill> spills;
-    for (int r = 0; r < c->world; r++) {
-        uint64_t pos = nlists, used_r = 0;
+    {
+        uint64_t pos = nlists;
         for (int k = 0; k < nlists; k++) {
-            const uint64_t n = all[(size_t)r * HDR + k];
-            const uint64_t f = std::min<uint64_t>(n, room - used_r);
+            const uint64_t n = v[k].count, f = fit[k];
             g->counts[k] += n;
-            if (f) g->pieces[k].push_back({c->recv_off + (size_t)r * c->cap + pos, c->recv_val + (size_t)r * c->cap + pos, f});
-            pos += f; used_r += f;
+            if (f) g->pieces[k].push_back({c->recv_off + pos, c->recv_val + pos, f});
+            pos += f;
             if (f < n) {
                 const uint64_t rest = n - f;
                 uint64_t *so = nullptr; uint32_t *sv = nullptr;
@@ -276,32 +334,26 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
                 g->owned.push_back(so);
                 if (cudaMallocAsync((void **)&sv, rest * sizeof(uint32_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
                 g->owned.push_back(sv);
-                if (r == 0) {
-                    if (cudaMemcpyAsync(so, v[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
-                        cudaMemcpyAsync(sv, v[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
-                        return bail(err(MMG_ERR_CUDA, "copying rank 0's overflow failed"));
-                } else {
-                    spills.push_back({r, so, sv, rest});
-                }
+                if (cudaMemcpyAsync(so, v[k].d_off + f, rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+                    cudaMemcpyAsync(sv, v[k].d_val + f, rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                    return bail(err(MMG_ERR_CUDA, "copying rank 0's overflow failed"));
                 g->pieces[k].push_back({so, sv, rest});
             }
         }
     }
-    if (!spills.empty()) {
-        // same order per peer as the sends (list by list, offsets then values); one group so that all peers stream at once
-        if (nccl().GroupStart() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupStart failed"));
-        for (const Spill &s : spills) {
-            if (nccl().Recv(s.off, s.n, ncclUint64, s.rank, c->comm, stream) != ncclSuccess ||
-                nccl().Recv(s.val, s.n, ncclUint32, s.rank, c->comm, stream) != ncclSuccess)
-                return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
-        }
-        if (nccl().GroupEnd() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupEnd failed"));
+    if (cudaEventCreateWithFlags(&g->landed, cudaEventDisableTiming) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "cudaEventCreate failed"));
+    if (c->world > 1) {
+        if (cudaMemcpy2DAsync(c->hdr_host, HDR * sizeof(uint64_t), c->recv_off, c->cap * sizeof(uint64_t),
+                              (size_t)nlists * sizeof(uint64_t), c->world, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaEventRecord(c->hdr_ready, stream) != cudaSuccess)
+            return bail(err(MMG_ERR_CUDA, "reading the gathered headers back failed"));
+        g->pending = true;
+        c->inflight = g;
+    } else {
+        if (cudaEventRecord(c->t1, stream) != cudaSuccess || cudaEventRecord(g->landed, stream) != cudaSuccess)
+            return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
+        c->timed = true;
     }
-    if (cudaEventRecord(c->t1, stream) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
-    c->timed = true;
-    if (cudaEventCreateWithFlags(&g->landed, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventRecord(g->landed, stream) != cudaSuccess)
-        return bail(err(MMG_ERR_CUDA, "cudaEventRecord failed"));
     for (int k = 0; k < nlists; k++) mmg_internal_results_free_on(lists[k], stream);
     *out = g;
     return MMG_OK;
@@ -311,6 +363,7 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
 // *ms_last (may be NULL) receives the device time of the last gather on this rank's gather stream.
 int mmg_comm_wait(mmg_comm *c, float *ms_last) {
     if (!c) return err(MMG_ERR_ARG, "null communicator");
+    if (c->inflight) complete_gather(c->inflight);
     CUC(cudaStreamSynchronize(c->stream));
     if (ms_last) {
         *ms_last = 0.f;
@@ -321,6 +374,7 @@ int mmg_comm_wait(mmg_comm *c, float *ms_last) {
 
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list) {
     if (!g || list < 0 || list >= g->nlists) return 0;
+    complete_gather(const_cast<mmg_gathered *>(g));
     return g->counts[list];
 }
 
@@ -357,6 +411,7 @@ int mmg_gathered_pieces(const mmg_gathered *g, int list, const uint64_t **offs, 
 
 void mmg_gathered_free(mmg_gathered *g) {
     if (!g) return;
+    complete_gather(g);                                       // the senders' overflow must still be received
     for (void *p : g->owned) cudaFreeAsync(p, g->stream);     // behind the receives that fill them
     if (g->landed) cudaEventDestroy(g->landed);
     delete g;
