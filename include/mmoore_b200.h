@@ -149,12 +149,15 @@ int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
  *   mmg_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller broadcasts it (any transport).
  *   mmg_comm_create    : collective over all ranks; capacity = entries of the fixed packed buffer.
  *   mmg_comm_gather    : collective; the `nlists` lists of one step (same nlists on every rank) go to
- *                        rank 0 in ONE grouped NCCL operation (+ point-to-point sends of whatever exceeds
- *                        the packed capacity; rank 0 posts the matching receives when the gathered object is
- *                        first used, at the latest at its next mmg_comm_gather / mmg_comm_wait call -- a send
- *                        that waits blocks only the gather stream).  The call only enqueues work.  *out is
- *                        non-NULL on rank 0 only.  The lists may be freed right after the call on every rank.
- *   mmg_comm_wait      : blocks until this rank's part of every gather so far has executed; *ms_last
+ *                        rank 0 in ONE grouped NCCL operation.  Whatever exceeds the packed capacity is set
+ *                        aside and travels at the start of every rank's NEXT call into the communicator
+ *                        (mmg_comm_gather or mmg_comm_wait), so no send ever waits for a peer outside a
+ *                        matching collective call.  The call only enqueues work.  *out is non-NULL on rank 0
+ *                        only; using it (count / copy / pieces / free) completes it, which for lists that
+ *                        did not fit needs the other ranks' next call -- call mmg_comm_wait on every rank
+ *                        first when in doubt.  The lists may be freed right after the call on every rank.
+ *   mmg_comm_wait      : collective; sends / receives what the last gather set aside and blocks until this
+ *                        rank's part of every gather so far has executed; *ms_last
  *                        (may be NULL) = device time of the last gather on this rank's gather stream.
  *   mmg_gathered_pieces: device-resident pieces (rank order == file order) of one gathered list. */
 typedef struct mmg_comm mmg_comm;

@@ -9,14 +9,15 @@
 //   1. every rank packs the lists of the step into a fixed-capacity buffer [counts | offsets ...]
 //      (+ a parallel buffer of table base values) and ONE grouped NCCL send/recv moves the packed
 //      buffers to rank 0;
-//   2. a rank whose lists do not fit enqueues point-to-point sends of the remainder right behind
-//      the packed send;
-//   3. rank 0 learns from the gathered headers what did not fit and posts the matching receives.  It
-//      does so LAZILY -- when the gathered object is first used, and at the latest at the start of
-//      the next gather (so receives and sends of consecutive gathers pair up in order) or in
-//      mmg_comm_wait -- which keeps the host of rank 0 off the critical path of a pipelined scan
-//      loop.  A send that waits for its receive blocks nothing but the dedicated gather stream:
-//      the scan streams and the collectives of other communicators run beside it.
+//   2. a rank whose lists do not fit copies the remainder into buffers of its own and sends it at the
+//      START OF ITS NEXT CALL into this communicator (the next gather, or mmg_comm_wait);
+//   3. rank 0 learns from the gathered headers what did not fit and posts the matching receives, also at
+//      the start of its next call (or when the gathered object is used first).  Sends and receives of
+//      consecutive gathers therefore pair up in order, nobody reads headers on the critical path of a
+//      pipelined scan loop, and -- the point of deferring the sends -- NO SEND EVER WAITS for a peer
+//      that is not inside the matching collective call: NCCL serialises the kernels of different
+//      communicators on a device, so a send left waiting for a lazily posted receive would stall the
+//      collectives of every other communicator (torch.distributed's, say) and deadlock the job.
 //
 // Everything runs on a dedicated, process-wide gather stream of the device: the scan streams never wait for NCCL, and a
 // list that is still being read by a send is released in gather-stream order (the results object is
@@ -106,6 +107,9 @@ struct mmg_comm {
     uint32_t *recv_val = nullptr;
     uint64_t *hdr_host = nullptr;   // pinned, rank 0: the headers of all ranks (HDR entries per rank)
     mmg_gathered *inflight = nullptr;   // rank 0: the gather whose headers have not been read yet
+    // ranks != 0: what the last gather could not pack, copied into owned buffers, sent at the start of the next call
+    struct Deferred { uint64_t *off; uint32_t *val; uint64_t n; };
+    std::vector<Deferred> deferred;
 };
 
 struct mmg_gathered {
@@ -118,28 +122,31 @@ struct mmg_gathered {
     cudaStream_t stream = nullptr;
     cudaEvent_t landed = nullptr;                 // every piece has arrived on rank 0
     bool waited = false;
-    // deferred part (rank 0): the other ranks' headers are read and their overflow received on first use
-    bool pending = false;
+    // deferred part (rank 0): the other ranks' headers are read on first use; the receives of their overflow are posted
+    // at the next collective point of the communicator (next gather / mmg_comm_wait) or by a blocking accessor
+    bool pending = false;                         // headers not read yet
+    bool posted = true;                           // receives of the overflow posted (nothing to post until the headers say so)
+    bool abandoned = false;                       // freed by the caller before it was complete: the communicator finishes and deletes it
+    struct Spill { int rank; uint64_t *off; uint32_t *val; uint64_t n; };
+    std::vector<Spill> spills;
     mmg_comm *comm = nullptr;
     int error = MMG_OK;
 };
 
 namespace {
 
-// rank 0: read the gathered headers of ranks 1.., build their piece lists, receive what did not fit
-int complete_gather(mmg_gathered *g) {
+// rank 0, stage 1: read the gathered headers of ranks 1.. and build their piece lists (host wait for the packed buffers;
+// no NCCL call, safe at any time)
+int read_headers(mmg_gathered *g) {
     if (!g->pending) return g->error;
     g->pending = false;
     mmg_comm *c = g->comm;
-    if (c->inflight == g) c->inflight = nullptr;
     cudaStream_t stream = g->stream;
     const int nlists = g->nlists;
     const uint64_t room = c->cap - (uint64_t)nlists;
     auto bail = [&](int code) { g->error = code; return code; };
     if (cudaEventSynchronize(c->hdr_ready) != cudaSuccess) return bail(err(MMG_ERR_CUDA, "waiting for the gathered headers failed"));
     const uint64_t *all = c->hdr_host;
-    struct Spill { int rank; uint64_t *off; uint32_t *val; uint64_t n; };
-    std::vector<Spill> spills;
     for (int r = 1; r < c->world; r++) {
         uint64_t pos = nlists, used_r = 0;
         for (int k = 0; k < nlists; k++) {
@@ -155,15 +162,35 @@ int complete_gather(mmg_gathered *g) {
                 g->owned.push_back(so);
                 if (cudaMallocAsync((void **)&sv, rest * sizeof(uint32_t), stream) != cudaSuccess) return bail(err(MMG_ERR_NOMEM, "spill buffer allocation failed"));
                 g->owned.push_back(sv);
-                spills.push_back({r, so, sv, rest});
+                g->spills.push_back({r, so, sv, rest});
                 g->pieces[k].push_back({so, sv, rest});
             }
         }
     }
-    if (!spills.empty()) {
+    g->posted = false;
+    return MMG_OK;
+}
+
+void delete_gathered(mmg_gathered *g) {
+    for (void *p : g->owned) cudaFreeAsync(p, g->stream);     // behind the receives that fill them
+    if (g->landed) cudaEventDestroy(g->landed);
+    delete g;
+}
+
+// rank 0, stage 2: post the receives of what the other ranks set aside (they send it at the start of their next call).
+// Only at a collective point of the communicator, or from an accessor that then blocks until the data has landed.
+int complete_gather(mmg_gathered *g) {
+    if (int rc = read_headers(g); rc != MMG_OK) return rc;
+    if (g->posted) return g->error;
+    g->posted = true;
+    mmg_comm *c = g->comm;
+    cudaStream_t stream = g->stream;
+    auto bail = [&](int code) { g->error = code; return code; };
+    if (c->inflight == g) c->inflight = nullptr;
+    if (!g->spills.empty()) {
         // same order per peer as the sends (list by list, offsets then values); one group so that all peers stream at once
         if (nccl().GroupStart() != ncclSuccess) return bail(err(MMG_ERR_CUDA, "ncclGroupStart failed"));
-        for (const Spill &sp : spills) {
+        for (const auto &sp : g->spills) {
             if (nccl().Recv(sp.off, sp.n, ncclUint64, sp.rank, c->comm, stream) != ncclSuccess ||
                 nccl().Recv(sp.val, sp.n, ncclUint32, sp.rank, c->comm, stream) != ncclSuccess)
                 return bail(err(MMG_ERR_CUDA, "receiving a spilled list failed"));
@@ -176,9 +203,42 @@ int complete_gather(mmg_gathered *g) {
     return MMG_OK;
 }
 
+// collective point of the communicator on rank 0: finish the gather that is still open
+void finish_inflight(mmg_comm *c) {
+    mmg_gathered *g = c->inflight;
+    if (!g) return;
+    complete_gather(g);
+    c->inflight = nullptr;
+    if (g->abandoned) delete_gathered(g);
+}
+
+// ranks != 0: send what the previous gather deferred (rank 0 posts the matching receives at the same point of ITS call)
+int flush_deferred(mmg_comm *c) {
+    if (c->deferred.empty()) return MMG_OK;
+    cudaStream_t stream = c->stream;
+    NC(nccl().GroupStart());
+    for (const auto &d : c->deferred) {
+        NC(nccl().Send(d.off, d.n, ncclUint64, 0, c->comm, stream));
+        NC(nccl().Send(d.val, d.n, ncclUint32, 0, c->comm, stream));
+    }
+    NC(nccl().GroupEnd());
+    for (const auto &d : c->deferred) { cudaFreeAsync(d.off, stream); cudaFreeAsync(d.val, stream); }
+    c->deferred.clear();
+    return MMG_OK;
+}
+
 void destroy_comm(mmg_comm *c) {
     if (!c) return;
-    if (c->inflight) complete_gather(c->inflight);
+    for (const auto &d : c->deferred) { cudaFreeAsync(d.off, c->stream); cudaFreeAsync(d.val, c->stream); }   // never sent: dropped
+    c->deferred.clear();
+    if (c->inflight) {                     // nobody will send its overflow any more: read the headers, drop the rest
+        mmg_gathered *g = c->inflight;
+        read_headers(g);
+        g->posted = true;
+        g->comm = nullptr;
+        c->inflight = nullptr;
+        if (g->abandoned) delete_gathered(g);
+    }
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
     cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
@@ -252,7 +312,8 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
     *out = nullptr;
     // the previous gather's headers live in the buffer this one reuses, and its overflow receives must be posted before
     // this gather's receives (sends and receives of a pair of ranks match in order)
-    if (c->inflight) complete_gather(c->inflight);
+    finish_inflight(c);
+    if (int rc = flush_deferred(c); rc != MMG_OK) return rc;
     cudaStream_t stream = c->stream;
     const uint64_t room = c->cap - (uint64_t)nlists;
     std::vector<mmg_results_view> v(nlists);
@@ -291,18 +352,20 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
     NC(nccl().GroupEnd());
 
     if (c->rank != 0) {
-        // what did not fit travels point-to-point; rank 0 posts the matching receives before ITS call returns
-        bool any = false;
-        for (int k = 0; k < nlists; k++) any = any || fit[k] < v[k].count;
-        if (any) {
-            NC(nccl().GroupStart());
-            for (int k = 0; k < nlists; k++) {
-                if (fit[k] < v[k].count) {
-                    NC(nccl().Send(v[k].d_off + fit[k], v[k].count - fit[k], ncclUint64, 0, c->comm, stream));
-                    NC(nccl().Send(v[k].d_val + fit[k], v[k].count - fit[k], ncclUint32, 0, c->comm, stream));
+        // what did not fit is copied aside (the lists may be freed right after this call) and sent at the next call
+        for (int k = 0; k < nlists; k++) {
+            if (fit[k] < v[k].count) {
+                const uint64_t rest = v[k].count - fit[k];
+                uint64_t *so = nullptr; uint32_t *sv = nullptr;
+                CUC(cudaMallocAsync((void **)&so, rest * sizeof(uint64_t), stream));
+                if (cudaMallocAsync((void **)&sv, rest * sizeof(uint32_t), stream) != cudaSuccess) {
+                    cudaFreeAsync(so, stream);
+                    return err(MMG_ERR_NOMEM, "spill buffer allocation failed");
                 }
+                c->deferred.push_back({so, sv, rest});
+                CUC(cudaMemcpyAsync(so, v[k].d_off + fit[k], rest * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+                CUC(cudaMemcpyAsync(sv, v[k].d_val + fit[k], rest * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
             }
-            NC(nccl().GroupEnd());
         }
         CUC(cudaEventRecord(c->t1, stream));
         c->timed = true;
@@ -363,7 +426,8 @@ int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mm
 // *ms_last (may be NULL) receives the device time of the last gather on this rank's gather stream.
 int mmg_comm_wait(mmg_comm *c, float *ms_last) {
     if (!c) return err(MMG_ERR_ARG, "null communicator");
-    if (c->inflight) complete_gather(c->inflight);
+    finish_inflight(c);
+    if (int rc = flush_deferred(c); rc != MMG_OK) return rc;
     CUC(cudaStreamSynchronize(c->stream));
     if (ms_last) {
         *ms_last = 0.f;
@@ -374,7 +438,7 @@ int mmg_comm_wait(mmg_comm *c, float *ms_last) {
 
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list) {
     if (!g || list < 0 || list >= g->nlists) return 0;
-    complete_gather(const_cast<mmg_gathered *>(g));
+    read_headers(const_cast<mmg_gathered *>(g));            // counts need the headers only
     return g->counts[list];
 }
 
@@ -411,10 +475,10 @@ int mmg_gathered_pieces(const mmg_gathered *g, int list, const uint64_t **offs, 
 
 void mmg_gathered_free(mmg_gathered *g) {
     if (!g) return;
-    complete_gather(g);                                       // the senders' overflow must still be received
-    for (void *p : g->owned) cudaFreeAsync(p, g->stream);     // behind the receives that fill them
-    if (g->landed) cudaEventDestroy(g->landed);
-    delete g;
+    // still open (headers unread or overflow not received): the senders will send their overflow at their next call all
+    // the same, so the communicator finishes this gather at ITS next collective point and deletes the object then
+    if (g->comm && g->comm->inflight == g && (g->pending || !g->posted)) { g->abandoned = true; return; }
+    delete_gathered(g);
 }
 
 }  // extern "C"

@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q):
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)      # a hung collective must not hang the suite: show where, then die
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
