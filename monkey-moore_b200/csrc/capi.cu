@@ -11,6 +11,7 @@
 #include "pattern.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -42,6 +43,7 @@ int fail(int code, const std::string &msg) {
 
 struct ScanError { int code; };
 
+std::atomic<int> g_live_comms{0};   // result-gather communicators alive in this process (comm.cu)
 int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everything tiles (testing)
 thread_local cudaStream_t g_user_stream = nullptr;   // set by mmg_set_stream: scans run on the caller's stream
 thread_local bool g_use_user_stream = false;
@@ -443,7 +445,10 @@ void enqueue_tiled(mmg_results *res) {
         const mmg_program *prog = res->rq.prog;
         const uint64_t hint_bytes = prog->last_bytes.load(), hint_events = prog->last_events.load();
         static const bool no_sparse = getenv("MMG_NO_SPARSE_RESOLVE") != nullptr;
-        t.sparse = !no_sparse && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
+        // Not beside a result gather: the fused kernel is launched cooperatively (its grid barrier needs every CTA
+        // resident), so it cannot share the SMs with an NCCL kernel the way the plain persistent grid does -- scans and
+        // gathers of a multi-GPU pipeline would take turns instead of overlapping.
+        t.sparse = !no_sparse && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
                    (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
     }
     X.fuse = t.sparse ? 1u : 0u;
@@ -919,6 +924,7 @@ void mmg_internal_results_free_on(const mmg_results *r, void *stream) {
     if (r) const_cast<mmg_results *>(r)->free_stream = static_cast<cudaStream_t>(stream);
 }
 void mmg_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+void mmg_internal_comm_alive(int delta) { g_live_comms += delta; }
 
 void *mmg_host_alloc(uint64_t nbytes) {
     void *p = nullptr;

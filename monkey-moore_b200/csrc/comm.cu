@@ -40,6 +40,7 @@ extern "C" int mmg_internal_results_view(const mmg_results *r, mmg_results_view 
 extern "C" void mmg_internal_results_free_on(const mmg_results *r, void *stream);
 extern "C" void *mmg_internal_gather_stream(void);
 extern "C" void mmg_internal_set_error(const char *msg);
+extern "C" void mmg_internal_comm_alive(int delta);
 
 namespace {
 
@@ -296,11 +297,15 @@ int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, m
     };
     const int rc = build();
     if (rc != MMG_OK) { destroy_comm(c); return rc; }
+    mmg_internal_comm_alive(+1);
     *out = c;
     return MMG_OK;
 }
 
-void mmg_comm_destroy(mmg_comm *c) { destroy_comm(c); }
+void mmg_comm_destroy(mmg_comm *c) {
+    if (c) mmg_internal_comm_alive(-1);
+    destroy_comm(c);
+}
 
 // Gathers `nlists` result lists (the searches of one step) of every rank to rank 0.
 // On rank 0 *out receives the gathered lists (rank order == ascending file offsets); elsewhere NULL.
