@@ -389,6 +389,25 @@ def measure(ctx, args, w, steps, warmup, headline):
             alone_n += 1
             res.close()
     torch.cuda.synchronize()
+    # sparse scans resolve inside the filter kernel (one launch): the same kernel WITHOUT that tail, for comparison
+    unf_ms, unf_bytes, unf_n, kinds = 0.0, 0, 0, set()
+    old = mm.set_path_override(4)
+    try:
+        for _ in range(4):
+            for prog, s_ in zip(progs, w.searches):
+                res = prog.engine_scan(next_blob(), w.block_size, big_endian=s_.big_endian, file_size=total_size,
+                                       first_block=b0, num_blocks=nb)
+                st = res.stats()
+                unf_ms += st["ms_filter"]; unf_bytes += st["bytes_scanned"] + 8 * res.count; unf_n += 1
+                res.close()
+    finally:
+        mm.set_path_override(old)
+    for prog, s_ in zip(progs, w.searches):
+        res = prog.engine_scan(next_blob(), w.block_size, big_endian=s_.big_endian, file_size=total_size,
+                               first_block=b0, num_blocks=nb)
+        kinds.add(res.stats()["resolve_kind"])
+        res.close()
+    torch.cuda.synchronize()
 
     # ---- e2e: host (pinned) buffers through the public call, H2D + scan + D2H of the results (+ gather)
     e2e = None
@@ -489,6 +508,8 @@ def measure(ctx, args, w, steps, warmup, headline):
                          "timing": "CUDA events around the filter launch on its stream, %d launches run alone after the "
                                    "timed region (inside it scans overlap on two streams)" % alone_n,
                          "achieved_in_timed_region": achieved_overlapped,
+                         "resolve_fused_into_this_kernel": kinds == {1},
+                         "filter_without_fused_resolve": (unf_bytes / unf_n) / (unf_ms / unf_n) / 1e6,
                          "whole_scan_frac": (alone_bytes / alone_n) / (alone_total / alone_n) / 1e6 / peak,
                          "pipeline_frac": value / world / peak},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity}

@@ -193,7 +193,8 @@ int mmg_set_stream(void *cuda_stream, int use_it);
 int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t first_byte, uint32_t byte_mask);
 
 /* Testing knob (returns the previous mode): 0 = automatic; 1 = force the per-chain generic kernels;
- * 2 = tiled path with exact evaluation of every window (no SWAR filter). */
+ * 2 = tiled path with exact evaluation of every window (no SWAR filter); 4 = tiled path, never resolve inside the
+ * filter kernel (sparse scans then run the separate resolve kernel like dense ones). */
 int mmg_set_path_override(int mode);
 
 #ifdef __cplusplus

@@ -448,7 +448,7 @@ void enqueue_tiled(mmg_results *res) {
         // Not beside a result gather: the fused kernel is launched cooperatively (its grid barrier needs every CTA
         // resident), so it cannot share the SMs with an NCCL kernel the way the plain persistent grid does -- scans and
         // gathers of a multi-GPU pipeline would take turns instead of overlapping.
-        t.sparse = !no_sparse && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
+        t.sparse = !no_sparse && g_path_override != 4 && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
                    (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
     }
     X.fuse = t.sparse ? 1u : 0u;
@@ -697,7 +697,8 @@ int mmg_set_stream(void *cuda_stream, int use_it) {
     return MMG_OK;
 }
 
-// testing knob: 0 auto, 1 force the per-chain generic kernels, 2 force exact evaluation of every window
+// testing knob: 0 auto, 1 force the per-chain generic kernels, 2 force exact evaluation of every window,
+// 4 never fuse the resolve into the filter kernel
 int mmg_set_path_override(int mode) {
     int old = g_path_override;
     g_path_override = mode;
