@@ -512,6 +512,7 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
         const uint64_t warps = ((uint64_t)G.nchunks + rounds - 1) / std::max<uint64_t>(rounds, 1);
         t.grid = (int)std::max<uint64_t>(1, (warps + 7) / 8);
         t.total_warps = (uint64_t)t.grid * 8;
+        G.static_chunks = 1;
     }
 
     // optimistic result capacity: what this pattern produced last time plus slack

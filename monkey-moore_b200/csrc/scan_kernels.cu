@@ -746,12 +746,20 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
     WarpState st;
     st.cursor = reg_lo;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
+    uint32_t static_round = 0;
 
     for (;;) {
-        // dynamic chunk scheduling: warps draw chunks from a global counter (balances the tail)
+        // dynamic chunk scheduling: warps draw chunks from a global counter (balances the tail).  Small inputs, where
+        // every warp gets the same few chunks anyway, take them round robin: the draw's round trip (~1 us) would be a
+        // tenth of the whole kernel
         uint32_t chunk = 0;
-        if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
-        chunk = __shfl_sync(FULL, chunk, 0);
+        if (G.static_chunks) {
+            chunk = warp + static_round * gridDim.x * MMG_FILTER_WARPS;
+            static_round++;
+        } else {
+            if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
+            chunk = __shfl_sync(FULL, chunk, 0);
+        }
         if (chunk >= G.nchunks) break;
 
         const uint32_t t0 = chunk * G.chunk_subs;
@@ -945,11 +953,17 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const bool always_dense = d2ok && (NK == 1 || P.nkeys == 1);
     uint32_t dense_left = always_dense ? 0xFFFFFFFFu : 0u;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
+    uint32_t static_round = 0;
 
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
-        chunk = __shfl_sync(FULL, chunk, 0);
+        if (G.static_chunks) {              // small inputs: round robin instead of a draw (see k_filter)
+            chunk = warp + static_round * gridDim.x * MMG_FILTER_WARPS;
+            static_round++;
+        } else {
+            if (lane == 0) chunk = (uint32_t)atomicAdd((unsigned long long *)&X.status[3], 1ull);
+            chunk = __shfl_sync(FULL, chunk, 0);
+        }
         if (chunk >= G.nchunks) break;
 
         const uint32_t t0 = chunk * G.chunk_subs;
