@@ -17,6 +17,10 @@ followed -- for N > 1 -- by the NCCL gather of the match lists to rank 0.
                (524288) and at the GUI's block (8 MiB)
     per_config: the other BASELINE configurations with the same fields (N = 1: cfg1, cfg3 at full size, cfg4 / cfg5 at
                their per-GPU slice; N > 1: cfg4 strong-scaled (16 GiB in total) and cfg5 (8 GiB per GPU))
+    single_chain: SURVEY 8f-4 -- the cfg4 bytes searched as ONE MonkeyMoore<uint16_t>::search chain: one call at N = 1
+               (and four slices through mmg_chain_*), one slice per rank through mmg_comm_search at N > 1 (the slice
+               maps cross the ranks in a 128-byte all-gather, the only exchange step of the whole path), checked against
+               the oracle's chain slice by slice
 
 Scaling: `weak` -- every rank scans `size` bytes, the file is n_gpus * size; `strong` -- the file is `size` bytes in
 total.  Either way the file is sharded by whole engine blocks (contiguous byte ranges + (L-1)*W bytes of overlap) and no
@@ -53,6 +57,8 @@ def parse():
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"])
     ap.add_argument("--size-mib", type=int, default=0, help="override the blob size (development)")
     ap.add_argument("--per-config", default="auto", help="auto | none | comma separated workload keys")
+    ap.add_argument("--chain", default="auto", choices=["auto", "on", "off"],
+                    help="single_chain object (cfg4 bytes as ONE search() chain, SURVEY 8f-4): auto = with the per_config run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -584,6 +590,135 @@ def verify(ctx, w, progs, blob, host_np, total_size, b0, nb, lo, hi, complete_st
             "digest": ["%016x" % d[2] for d in mine]}
 
 
+def measure_chain(ctx, args):
+    """SURVEY 8f-4: the cfg4 bytes searched as ONE MonkeyMoore<uint16_t>::search chain (even alignment, LE) instead of
+    independent engine blocks.  N = 1: the whole buffer in one call, and in four slices through mmg_chain_*;
+    N > 1: one slice per rank through mmg_comm_search (the slice maps cross the ranks in one 128-byte all-gather),
+    lists gathered to rank 0.  Parity: every rank's list against the oracle's chain over the same slice entered with
+    the same phase, the oracle's exit phase of rank r against the entry phase rank r + 1 was given, entry 0 = 0."""
+    torch, mm, dist, comm = ctx.torch, ctx.mm, ctx.dist, ctx.comm
+    rank, world = ctx.rank, ctx.world
+    import monkey_moore_b200.workloads as wl
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import Oracle, digest
+
+    w = wl.WORKLOADS["cfg4"]
+    s = w.searches[0]
+    total = (w.single_gpu_size or w.size) if world == 1 else w.size
+    if args.size_mib:
+        total = args.size_mib << 20
+    W = w.bits // 8
+    prog = mm.Program(w.bits, **s.pattern)
+    n = total // W
+    tail = prog.keyword_len - 1
+    per = (n // world) * W // 4096 * 4096 // W
+    first = rank * per
+    owned = per if rank < world - 1 else n - first
+    avail = owned if rank == world - 1 else owned + tail
+    blob = wl.device_blob(w, first_byte=first * W, nbytes=avail * W, total_size=total)
+    mm.set_stream(ctx.stream.cuda_stream, True)
+
+    def barrier():
+        if world > 1:
+            comm.wait()
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(keep=None):
+        if world > 1:
+            res = comm.search(prog, blob, owned, first)
+            g = comm.gather([res], lazy=True)
+            if keep is not None:
+                keep.append((res, g))
+                return
+            res.close()
+            if g is not None:
+                g.close()
+        else:
+            res = prog.search(blob)
+            if keep is not None:
+                keep.append((res, None))
+                return
+            res.count
+            res.close()
+
+    def timed(fn, steps):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
+
+    steps = 5
+    sec = timed(step, steps)
+    out = {"workload": "cfg4 bytes as ONE MonkeyMoore<uint16_t>::search chain (even alignment)", "bytes": total,
+           "slices": world, "steps": steps, "value": round(total * steps / sec / 1e9, 1), "unit": "GB/s",
+           "ms_per_step": round(sec / steps * 1e3, 3),
+           "timing": "host clock around the steps, barrier + synchronize on both sides, max over ranks (every step waits "
+                     "for the map exchange on the host)" if world > 1 else "host clock, synchronize on both sides"}
+    if world == 1:
+        def sliced():
+            parts = prog.search_sliced(blob, (n // 4) * W // 4096 * 4096 // W)
+            for p_ in parts:
+                p_.count
+                p_.close()
+        sec4 = timed(sliced, steps)
+        out["four_slices_one_gpu"] = {"value": round(total * steps / sec4 / 1e9, 1), "ms_per_step": round(sec4 / steps * 1e3, 3)}
+    if args.no_verify:
+        return out
+    # ---- parity
+    keep = []
+    step(keep)
+    res, g = keep[0]
+    off, val = res.arrays()
+    entry = res.stats()["chain_entry"]
+    if not fits_in_host_ram(avail * W * (min(world, torch.cuda.device_count()))):
+        out["parity"] = {"checked": False, "note": "host copy of the slices would not fit"}
+        return out
+    host = blob.cpu().numpy().view(np.uint16)
+    o = Oracle(w.bits, keyword=s.pattern.get("keyword"), wildcard=s.pattern.get("wildcard", 0), char_seq=s.pattern.get("char_seq", ()))
+    t0 = time.perf_counter()
+    opos, oval, oexit = o.search_slice(host, entry, owned)
+    cpu_sec = time.perf_counter() - t0
+    same = off.tolist() == (opos + np.uint64(first)).tolist() and val.tolist() == oval.tolist()
+    ok = {"rank_lists_equal_oracle": bool(same), "matches": int(len(off))}
+    if world > 1:
+        t = torch.tensor([entry, oexit - owned if rank < world - 1 else 0, int(same), len(off)], dtype=torch.int64, device="cuda")
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        rows = [p_.tolist() for p_ in parts]
+        linked = rows[0][0] == 0 and all(rows[r + 1][0] == rows[r][1] for r in range(world - 1))
+        ok = {"rank_lists_equal_oracle": all(r[2] == 1 for r in rows), "entry_phases": [r[0] for r in rows],
+              "entry_phases_equal_oracle_exits": bool(linked), "matches": sum(r[3] for r in rows)}
+        if rank == 0:
+            goff, _gval = g.fetch()[0]
+            ok["gathered_count"] = int(len(goff))
+            ok["gathered_ascending"] = bool(np.all(goff[1:] > goff[:-1])) if len(goff) > 1 else True
+            ok["gathered_equals_sum_of_ranks"] = int(len(goff)) == ok["matches"]
+            ok["gathered_prefix_equals_rank0_list"] = goff[: len(off)].tolist() == off.tolist()
+            g.close()
+    else:
+        parts = prog.search_sliced(blob, (n // 4) * W // 4096 * 4096 // W)
+        soff = np.concatenate([p_.arrays()[0] for p_ in parts])
+        ok["four_slices_equal_whole"] = soff.tolist() == off.tolist()
+        ok["entry_phases"] = [p_.stats()["chain_entry"] for p_ in parts]
+        for p_ in parts:
+            p_.close()
+    res.close()
+    ok["oracle_cpu_gbs_1thread"] = round(owned * W / cpu_sec / 1e9, 2)
+    out["parity"] = ok
+    barrier()
+    return out
+
+
 def run_ours(args):
     import torch
 
@@ -628,6 +763,14 @@ def run_ours(args):
             r["workload"] = key
             r["unit"] = "GB/s"
             per.append(r)
+    chain = None
+    if args.chain == "on" or (args.chain == "auto" and per_config_keys(args, ctx.world)):   # auto: with the default full run
+        try:
+            chain = measure_chain(ctx, args)
+        except Exception as e:
+            if ctx.world > 1:
+                raise
+            chain = {"error": "%s: %s" % (type(e).__name__, e)}
     if ctx.rank == 0:
         line = {"metric": METRIC, "value": head["value"], "unit": "GB/s", "n_gpus": ctx.world, "steps": head["steps"],
                 "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
@@ -638,6 +781,8 @@ def run_ours(args):
             line[k] = head[k]
         if per:
             line["per_config"] = per
+        if chain is not None:
+            line["single_chain"] = chain
         print(json.dumps(line))
     if ctx.world > 1:
         ctx.comm.close()

@@ -78,6 +78,31 @@ void mmg_program_table(const mmg_program *p, uint32_t v0, uint32_t v1, uint32_t 
  * Match positions are element indices, ascending. */
 int mmg_search(const mmg_program *p, const void *data, uint64_t data_len, int mem, mmg_results **out);
 
+/* MonkeyMoore<Ty>::search over a buffer that is cut into SLICES (one per GPU, or per call when the buffer
+ * does not fit): still ONE chain from element 0 of the whole buffer (src/core/monkey_moore.cpp:316-546), so
+ * where the chain enters a slice depends on everything before it.  Every slice is scanned without that
+ * knowledge; what it hands on is its MAP: for each possible entry phase (distance of the first chain position
+ * from the slice's first element, < mmg_program_max_jump) the phase with which the chain enters the next slice.
+ *
+ *   mmg_chain_begin   enqueues filter + maps of one slice.  data[0] is element first_element of the buffer; the
+ *                     slice OWNS the windows that start in its first owned_len elements; avail_len >= owned_len
+ *                     elements are present: owned_len + keyword_len - 1 (or more) when another slice follows --
+ *                     owned_len * sizeof(Ty) must then be a multiple of 4096 -- and exactly owned_len for the
+ *                     last slice.  *out is a results object that is not yet usable as one.
+ *   mmg_chain_map     waits for the map of the slice: map[e] = exit phase for entry phase e, *n entries.
+ *   mmg_chain_entry   host arithmetic: the entry phase of slice `nslices` given the maps of slices 0..nslices-1
+ *                     (maps + k * stride); 0 for the first slice.
+ *   mmg_chain_finish  enqueues the rest of the scan with the slice's entry phase; from then on *out behaves like
+ *                     the results of mmg_engine_scan_async (element indices of the WHOLE buffer, ascending).
+ * The concatenation of the slices' lists in slice order equals mmg_search over the whole buffer.
+ * mmg_comm_search (below) runs this protocol across the ranks of a communicator. */
+int mmg_chain_begin(const mmg_program *p, const void *data, uint64_t owned_len, uint64_t avail_len, int mem,
+                    uint64_t first_element, mmg_results **out);
+int mmg_chain_map(mmg_results *r, uint8_t *map, int capacity, int *n);
+uint32_t mmg_chain_entry(const uint8_t *maps, int stride, int nslices);
+int mmg_chain_finish(mmg_results *r, uint32_t entry_phase);
+int mmg_program_max_jump(const mmg_program *p);      /* number of entry phases of a slice (<= 128) */
+
 /* The chunk engine of mmoore::SearchEngine<T>::run WITHOUT file I/O, previews and callbacks:
  *   compute_search_blocks          src/core/search_engine.cpp:218-253
  *   per-block, per-alignment scan  src/core/search_engine.cpp:129-159
@@ -136,7 +161,7 @@ typedef struct mmg_scan_stats {
     uint64_t events;         /* candidate windows that needed exact evaluation */
     uint64_t bytes_scanned;
     uint32_t resolve_kind;   /* 0 resolve kernel, 1 resolved inside the filter kernel (sparse scans), 2 that was tried and the resolve kernel re-ran */
-    uint32_t reserved;
+    uint32_t chain_entry;    /* chain slices (mmg_chain_*, mmg_comm_search): the entry phase the slice was finished with */
 } mmg_scan_stats;
 int mmg_results_stats(const mmg_results *r, mmg_scan_stats *out);
 
@@ -167,6 +192,13 @@ int mmg_comm_create(const void *id128, int rank, int world, uint64_t capacity, m
 void mmg_comm_destroy(mmg_comm *c);
 int mmg_comm_gather(mmg_comm *c, const mmg_results *const *lists, int nlists, mmg_gathered **out);
 int mmg_comm_wait(mmg_comm *c, float *ms_last);
+/* One chain over a buffer that is spread over the ranks (rank r holds slice r, see mmg_chain_begin): every rank
+ * scans its slice, the slice maps are exchanged with one all-gather of max_jump bytes per rank -- the only step
+ * of the whole path where ranks depend on each other -- and every rank finishes its slice with the entry phase
+ * composed from the maps of the ranks before it.  *out holds this rank's part of the result of
+ * MonkeyMoore<Ty>::search on the whole buffer; mmg_comm_gather concatenates the parts on rank 0.  Collective. */
+int mmg_comm_search(mmg_comm *c, const mmg_program *p, const void *data, uint64_t owned_len, uint64_t avail_len,
+                    int mem, uint64_t first_element, mmg_results **out);
 uint64_t mmg_gathered_count(const mmg_gathered *g, int list);
 int mmg_gathered_copy(const mmg_gathered *g, int list, uint64_t *offsets, uint32_t *values);
 int mmg_gathered_pieces(const mmg_gathered *g, int list, const uint64_t **offs, const uint32_t **vals, uint64_t *ns, int cap);

@@ -36,6 +36,7 @@ C_ABI_SYMBOLS = [
     "mmg_results_stats", "mmg_set_path_override", "mmg_synth_fill", "mmg_set_stream", "mmg_host_alloc", "mmg_host_free", "mmg_host_copy",
     "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_comm_wait",
     "mmg_gathered_count", "mmg_gathered_copy", "mmg_gathered_pieces", "mmg_gathered_free",
+    "mmg_chain_begin", "mmg_chain_map", "mmg_chain_entry", "mmg_chain_finish", "mmg_program_max_jump", "mmg_comm_search",
 ]
 
 _u32p = C.POINTER(C.c_uint32)
@@ -46,7 +47,7 @@ _i16p = C.POINTER(C.c_int16)
 class ScanStats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_filter", C.c_float), ("ms_h2d", C.c_float),
                 ("launches", C.c_uint32), ("fast_path", C.c_uint32), ("events", C.c_uint64),
-                ("bytes_scanned", C.c_uint64), ("resolve_kind", C.c_uint32), ("reserved", C.c_uint32)]
+                ("bytes_scanned", C.c_uint64), ("resolve_kind", C.c_uint32), ("chain_entry", C.c_uint32)]
 
 
 class MMError(RuntimeError):
@@ -114,6 +115,14 @@ def lib():
         l.mmg_gathered_copy.argtypes = [C.c_void_p, C.c_int, _u64p, _u32p]
         l.mmg_gathered_free.argtypes = [C.c_void_p]
         l.mmg_synth_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+        l.mmg_chain_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
+        l.mmg_chain_map.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        l.mmg_chain_entry.restype = C.c_uint32
+        l.mmg_chain_entry.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        l.mmg_chain_finish.argtypes = [C.c_void_p, C.c_uint32]
+        l.mmg_program_max_jump.argtypes = [C.c_void_p]
+        l.mmg_comm_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
+                                      C.POINTER(C.c_void_p)]
         _lib = l
     return _lib
 
@@ -230,6 +239,43 @@ class Results:
         return [self._program.table(int(v[0]), int(v[1])) for v in val]
 
 
+def chain_entry(maps):
+    """Entry phase of the slice that follows the slices whose maps are given (``mmg_chain_entry``)."""
+    if not maps:
+        return 0
+    stride = max(len(m) for m in maps)
+    raw = b"".join(bytes(m) + bytes(stride - len(m)) for m in maps)
+    return int(lib().mmg_chain_entry(raw, stride, len(maps)))
+
+
+class ChainSlice:
+    """One slice of a longer chain between ``mmg_chain_begin`` and ``mmg_chain_finish``."""
+
+    def __init__(self, handle, program, keep=None):
+        self._h, self.program, self._keep = handle, program, keep
+
+    def map(self):
+        """Exit phase for every entry phase (waits for the first half of the scan)."""
+        buf = C.create_string_buffer(128)
+        n = C.c_int(0)
+        _check(lib().mmg_chain_map(self._h, buf, 128, C.byref(n)))
+        return bytes(buf.raw[:n.value])
+
+    def finish(self, entry_phase):
+        """Enqueues the second half -> :class:`Results` (element indices of the whole buffer)."""
+        h, self._h = self._h, None
+        res = Results(h, self.program, self._keep)
+        _check(lib().mmg_chain_finish(h, int(entry_phase)))
+        return res
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mmg_results_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class Comm:
     """NCCL communicator of the C-ABI for the result gather (one process per GPU).
 
@@ -264,6 +310,18 @@ class Comm:
             return out.fetch() if fetch else out.counts()
         finally:
             out.close()
+
+    def search(self, program, data, owned_len, first_element):
+        """Collective: ``MonkeyMoore<Ty>::search`` over ONE buffer that is spread over the ranks.  ``data`` is this
+        rank's slice: ``owned_len`` elements whose windows it owns, followed -- on every rank but the last -- by at
+        least ``keyword_len - 1`` elements of the next rank's slice; its first element is element
+        ``first_element`` of the whole buffer.  Returns this rank's part of the match list (element indices of
+        the whole buffer); ``gather`` concatenates the parts on rank 0."""
+        ptr, nbytes, mem, keep = program._pointer(data)
+        h = C.c_void_p()
+        _check(lib().mmg_comm_search(self._h, program._h, ptr, int(owned_len), nbytes // (program.bits // 8), mem,
+                                     int(first_element), C.byref(h)))
+        return Results(h, program, keep)
 
     def wait(self):
         """Blocks until this rank's part of every gather so far has executed -> device ms of the last gather."""
@@ -368,6 +426,41 @@ class Program:
         h = C.c_void_p()
         _check(lib().mmg_search(self._h, ptr, nbytes // (self.bits // 8), mem, C.byref(h)))
         return Results(h, self)
+
+    @property
+    def max_jump(self):
+        """Number of entry phases of a chain slice (== largest advance of the pattern)."""
+        return lib().mmg_program_max_jump(self._h)
+
+    def chain_begin(self, data, owned_len, first_element):
+        """First half of a slice of a longer chain (``mmg_chain_begin``): ``data`` = ``owned_len`` owned elements plus,
+        unless it is the last slice, at least ``keyword_len - 1`` elements of the next one."""
+        ptr, nbytes, mem, keep = self._pointer(data)
+        h = C.c_void_p()
+        _check(lib().mmg_chain_begin(self._h, ptr, int(owned_len), nbytes // (self.bits // 8), mem, int(first_element), C.byref(h)))
+        return ChainSlice(h, self, keep)
+
+    def search_sliced(self, data, slice_len):
+        """``search(data)`` computed slice by slice on this GPU (all slices in flight at once): the single-GPU
+        rehearsal of ``Comm.search``, and the way to search one chain through a buffer in pieces.
+        ``slice_len`` elements per slice, a multiple of ``4096 / sizeof(Ty)``."""
+        W = self.bits // 8
+        ptr, nbytes, mem, keep = self._pointer(data)
+        n = nbytes // W
+        tail = self.keyword_len - 1
+        slices = []
+        first = 0
+        while first < n:
+            owned = min(slice_len, n - first)
+            if n - (first + owned) <= tail:          # no window fits into what would remain: this is the last slice
+                owned = n - first
+            avail = owned if first + owned >= n else owned + tail
+            h = C.c_void_p()
+            _check(lib().mmg_chain_begin(self._h, ptr + first * W, owned, avail, mem, first, C.byref(h)))
+            slices.append(ChainSlice(h, self, keep))
+            first += owned
+        maps = [s.map() for s in slices]
+        return [s.finish(chain_entry(maps[:k])) for k, s in enumerate(slices)]
 
     def engine_scan(self, data, block_size, big_endian=False, file_size=None, first_block=0, num_blocks=0,
                     asynchronous=False):

@@ -258,6 +258,7 @@ struct ScanRequest {
     bool big_endian;
     uint64_t base_offset;
     uint32_t report_shift;
+    bool chain = false;       // slice of a longer chain (mmg_chain_*): B = bytes whose windows this slice owns
 };
 
 // what a launched-but-not-yet-finished tiled scan needs to be completed (or re-run after an overflow)
@@ -265,6 +266,7 @@ struct TiledState {
     MmgGeom G{};
     MmgScratch X{};
     int lag_bytes = 0, grid = 0;
+    int chain = 0;                // slice of a longer chain: CHAIN_MAPS while the entry phase is unknown, CHAIN_FULL afterwards
     bool sparse = false;          // resolved inside the filter kernel (fused sparse resolve): no per-sub-tile match bookkeeping exists
     uint64_t total_warps = 0, per_warp = 0, cap = 0;
     uint64_t generation = 0;      // workspace generation of this scan's last enqueue
@@ -288,8 +290,14 @@ struct mmg_results {
     Arena *arena = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start (host input only), scan start, after filter, end
     uint64_t *status_host = nullptr;                            // pinned slot receiving X.status
+    uint8_t *chain_map = nullptr;                               // pinned [2][jp]: map of a chain slice (mmg_chain_*)
+    Workspace *own_ws = nullptr;                                // chain slices keep their events between the two halves: a
+                                                                // workspace of their own, not the lane's (several slices are in flight at once)
+    int chain_stage = 0;                                        // 0 not a chain slice, 1 maps enqueued, 2 maps read, 3 resolve enqueued
     uint32_t launches = 0;
 };
+
+enum { CHAIN_MAPS = 1, CHAIN_FULL = 2 };
 
 namespace {
 
@@ -297,6 +305,7 @@ namespace {
 std::mutex g_pool_mutex;
 std::vector<cudaEvent_t> g_event_pool;
 std::vector<uint64_t *> g_slot_pool;
+std::vector<uint8_t *> g_map_pool;
 
 cudaEvent_t take_event() {
     {
@@ -320,10 +329,31 @@ uint64_t *take_slot() {
     return s;
 }
 
+uint8_t *take_map() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_map_pool.empty()) {
+        uint8_t *block = nullptr;
+        CU(cudaHostAlloc((void **)&block, 16 * 2 * MMG_MAXL, cudaHostAllocMapped | cudaHostAllocPortable));   // k_slicemap writes the slice's map here
+        for (int i = 0; i < 16; i++) g_map_pool.push_back(block + 2 * MMG_MAXL * i);
+    }
+    uint8_t *m = g_map_pool.back();
+    g_map_pool.pop_back();
+    return m;
+}
+
 void release_inflight(mmg_results *r) {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
     for (auto &e : r->ev) { if (e) g_event_pool.push_back(e); e = nullptr; }
     if (r->status_host) { g_slot_pool.push_back(r->status_host); r->status_host = nullptr; }
+    if (r->chain_map) { g_map_pool.push_back(r->chain_map); r->chain_map = nullptr; }
+    if (r->own_ws) {
+        Workspace *w = r->own_ws;
+        if (w->zero) cudaFreeAsync(w->zero, r->stream);
+        if (w->scratch) cudaFreeAsync(w->scratch, r->stream);
+        if (w->ev) cudaFreeAsync(w->ev, r->stream);
+        delete w;
+        r->own_ws = nullptr;
+    }
     delete r->arena;
     r->arena = nullptr;
 }
@@ -411,8 +441,10 @@ void enqueue_tiled(mmg_results *res) {
     const size_t o_mcount = carve((size_t)G.nsub * sizeof(uint32_t));
     const size_t o_mbase = carve((size_t)G.nsub * sizeof(uint64_t));
     const size_t jp = (size_t)((P.Jmax + 15) / 16 * 16);
-    const size_t o_segmap = carve(G.segs_per_block > 1 ? (size_t)G.nseg * 2 * jp : 0);
-    const size_t o_segphase = carve(G.segs_per_block > 1 ? (size_t)G.nseg * 2 : 0);
+    const bool segmented = G.segs_per_block > 1 || t.chain;
+    const size_t o_segmap = carve(segmented ? (size_t)G.nseg * 2 * jp : 0);
+    const size_t o_segphase = carve(segmented ? (size_t)G.nseg * 2 : 0);
+    const size_t o_rangemap = carve(t.chain || mmg_resolve_two_level(G) ? (size_t)128 * 2 * jp : 0);
     const size_t scratch_need = off;
     const bool zero_grew = zero_need > ws.zero_bytes;
     grow(ws.zero, ws.zero_bytes, zero_need, stream, true);
@@ -434,6 +466,8 @@ void enqueue_tiled(mmg_results *res) {
     X.mbase = reinterpret_cast<uint64_t *>(ws.scratch + o_mbase);
     X.segmap = ws.scratch + o_segmap;
     X.segphase = ws.scratch + o_segphase;
+    X.rangemap = ws.scratch + o_rangemap;
+    X.slicemap_host = res->chain_map;
     X.ev = ws.ev;
     X.ev_per_warp = (uint32_t)t.per_warp;
     X.host_status = res->status_host;             // pinned + mapped: same address on the device (UVA)
@@ -448,16 +482,30 @@ void enqueue_tiled(mmg_results *res) {
         // Not beside a result gather: the fused kernel is launched cooperatively (its grid barrier needs every CTA
         // resident), so it cannot share the SMs with an NCCL kernel the way the plain persistent grid does -- scans and
         // gathers of a multi-GPU pipeline would take turns instead of overlapping.
-        t.sparse = !no_sparse && g_path_override != 4 && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
+        t.sparse = !t.chain && !no_sparse && g_path_override != 4 && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
                    (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
     }
     X.fuse = t.sparse ? 1u : 0u;
     if (res->launches == 0) CU(cudaEventRecord(res->ev[1], stream));      // ev[1] -> ev[2] brackets the filter kernel alone
     CU(mmg_launch_filter(P, t.G, X, t.lag_bytes, t.grid, stream));
     if (res->launches == 0) CU(cudaEventRecord(res->ev[2], stream));
+    if (t.chain) {
+        // slice of a longer chain: the slice's map first; the resolve half follows here only when the entry phase is
+        // already known (a re-run after mmg_chain_finish), otherwise mmg_chain_finish enqueues it.  Until the resolve
+        // kernel has run nobody restores the zero state: the workspace stays marked dirty.
+        CU(mmg_launch_chain_maps(P, t.G, X, stream));
+        res->launches += 4;
+        if (t.chain == CHAIN_FULL) {
+            CU(mmg_launch_chain_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
+            res->launches += 2;
+            ws.dirty = false;
+        }
+        t.generation = ++ws.generation;
+        return;
+    }
     if (!t.sparse) CU(mmg_launch_resolve(P, t.G, X, res->d_off, res->d_val, t.cap, stream));
     ws.dirty = false;
-    res->launches += t.sparse ? 1 : (t.G.segs_per_block > 1 ? 4 : 2);
+    res->launches += t.sparse ? 1 : (t.G.segs_per_block > 1 ? (mmg_resolve_two_level(t.G) ? 5 : 4) : 2);
     t.generation = ++ws.generation;
 }
 
@@ -474,8 +522,11 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     G.data = rq.d_bytes; G.S = rq.S; G.base_offset = rq.base_offset;
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * W; G.npads = rq.npads;
     G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
-    if (rq.nblocks == 1) G.B = ((std::max<uint64_t>(std::max(rq.S, rq.B), 1) + MMG_SUBTILE - 1) / MMG_SUBTILE) * MMG_SUBTILE;
+    // (a chain slice that is continued by another one owns exactly B bytes of windows; the bytes behind are overlap)
+    const bool continued = rq.chain && rq.S > rq.B;
+    if (rq.nblocks == 1 && !continued) G.B = ((std::max<uint64_t>(std::max(rq.S, rq.B), 1) + MMG_SUBTILE - 1) / MMG_SUBTILE) * MMG_SUBTILE;
     else G.B = rq.B;
+    if (rq.chain) { t.chain = CHAIN_MAPS; G.chain = 1; }
     const uint64_t spb = G.B / MMG_SUBTILE;
     const uint64_t last_off = (rq.nblocks - 1) * G.B;
     const uint64_t nsub64 = (rq.nblocks - 1) * spb + (rq.S - last_off + MMG_SUBTILE - 1) / MMG_SUBTILE;
@@ -554,7 +605,7 @@ void finish_tiled(mmg_results *res) {
         res->stats.resolve_kind = 2;
         if (t.generation == t.ws->generation) {
             CU(mmg_launch_resolve(P, t.G, t.X, res->d_off, res->d_val, t.cap, stream));
-            res->launches += t.G.segs_per_block > 1 ? 3 : 1;
+            res->launches += t.G.segs_per_block > 1 ? (mmg_resolve_two_level(t.G) ? 4 : 3) : 1;
         } else {
             res->rq.prog->last_events = ev_total;       // so that the re-run picks the general kernel
             res->rq.prog->last_bytes = res->rq.S;
@@ -613,7 +664,8 @@ int finish_scan(mmg_results *r) {
 
 // Enqueues a scan on the calling thread's stream; *out is a pending results object.
 int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int mem, uint64_t B, uint64_t nblocks,
-                uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, mmg_results **out) {
+                uint32_t npads, bool big_endian, uint64_t base_offset, uint32_t report_shift, mmg_results **out,
+                bool chain = false) {
     *out = nullptr;
     mmg_results *res = new mmg_results();
     try {
@@ -648,26 +700,49 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
             throw ScanError{fail(MMG_ERR_ARG, "device pointer must be 16-byte aligned")};
         }
         if (mem == MMG_MEM_HOST) CU(cudaEventRecord(res->ev[1], stream));      // end of the copy (re-recorded before the filter)
-        res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift};
+        res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift, chain};
         const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
-        res->tiled = regular && g_path_override != 1;
+        res->tiled = regular && (g_path_override != 1 || chain);
         res->stats.fast_path = res->tiled;
+        if (chain) res->chain_map = take_map();
         if (res->tiled) {
-            launch_tiled(res, dev, lane.ws);
+            if (chain) res->own_ws = new Workspace();
+            launch_tiled(res, dev, chain ? *res->own_ws : lane.ws);
         } else {
             CU(cudaEventRecord(res->ev[1], stream));
             run_generic(res->rq, stream, *res->arena, res, res->launches);
             CU(cudaEventRecord(res->ev[2], stream));
         }
         CU(cudaEventRecord(res->ev[3], stream));
-        res->pending = true;
+        if (chain) res->chain_stage = 1;         // completed by mmg_chain_map / mmg_chain_finish, not by finish_scan
+        else res->pending = true;
         *out = res;
         return MMG_OK;
     } catch (const ScanError &e) {
         cudaGetLastError();
         release_inflight(res);
+        res->chain_stage = 0;
         mmg_results_free(res);
         return e.code;
+    }
+}
+
+// chain slice, first half: waits for the slice's map; grows the event buffer and re-runs on overflow
+void finish_chain_maps(mmg_results *res) {
+    TiledState &t = res->t;
+    cudaStream_t stream = res->stream;
+    CU(cudaEventSynchronize(res->ev[3]));
+    volatile uint64_t *status = res->status_host;
+    for (int attempt = 0; status[0] > t.per_warp; attempt++) {
+        if (attempt >= 3) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer overflow persists")};
+        t.per_warp = status[0] + status[0] / 4 + 64;
+        if (t.per_warp * t.total_warps > 0xFFFFFFF0ull) throw ScanError{fail(MMG_ERR_NOMEM, "event buffer would exceed 2^32 entries")};
+        {
+            std::lock_guard<std::mutex> lock(res->dev->mu);
+            enqueue_tiled(res);
+            CU(cudaEventRecord(res->ev[3], stream));
+        }
+        CU(cudaStreamSynchronize(stream));
     }
 }
 
@@ -730,6 +805,7 @@ int mmg_program_create_values(const int16_t *values, int n, int elem_bits, mmg_p
 
 void mmg_program_free(mmg_program *p) { delete p; }
 int mmg_program_keyword_len(const mmg_program *p) { return p->dev.L; }
+int mmg_program_max_jump(const mmg_program *p) { return p ? p->dev.Jmax : 0; }
 int mmg_program_mode(const mmg_program *p) { return p->mode; }
 
 int mmg_program_table_size(const mmg_program *p) {
@@ -775,6 +851,78 @@ int mmg_search(const mmg_program *p, const void *data, uint64_t data_len, int me
     const uint32_t W = p->dev.W;
     const uint64_t nbytes = data_len * W;
     return run_scan(p, data, nbytes, mem, nbytes, nbytes ? 1 : 0, 1, false, 0, W == 2 ? 1 : 0, false, out);
+}
+
+int mmg_chain_begin(const mmg_program *p, const void *data, uint64_t owned_len, uint64_t avail_len, int mem,
+                    uint64_t first_element, mmg_results **out) {
+    if (!p || !out || (!data && avail_len)) return fail(MMG_ERR_ARG, "null argument");
+    if (avail_len < owned_len) return fail(MMG_ERR_ARG, "avail_len smaller than owned_len");
+    const uint32_t W = p->dev.W;
+    const uint64_t owned = owned_len * W, avail = std::min(avail_len, owned_len + (uint64_t)(p->dev.L - 1)) * W;
+    if (avail > owned && (owned == 0 || owned % MMG_SUBTILE != 0))
+        return fail(MMG_ERR_ARG, "a slice that is continued must own a positive multiple of 4096 bytes");
+    if (owned == 0) return fail(MMG_ERR_ARG, "empty slice");
+    if (avail_len > owned_len && avail_len < owned_len + (uint64_t)(p->dev.L - 1))
+        return fail(MMG_ERR_ARG, "a slice that is continued needs keyword_len - 1 elements of the next slice behind it");
+    return launch_scan(p, data, avail, mem, owned, 1, 1, false, first_element * W, W == 2 ? 1 : 0, out, true);
+}
+
+int mmg_chain_map(mmg_results *r, uint8_t *map, int capacity, int *n) {
+    if (!r || !map || r->chain_stage == 0) return fail(MMG_ERR_ARG, "not a chain slice");
+    if (r->error != MMG_OK) return r->error;
+    const int J = r->rq.prog->dev.Jmax;
+    if (capacity < J) return fail(MMG_ERR_ARG, "map buffer too small");
+    if (r->chain_stage == 1) {
+        try {
+            finish_chain_maps(r);
+        } catch (const ScanError &e) {
+            r->error = e.code;
+            cudaGetLastError();
+            return e.code;
+        }
+        r->chain_stage = 2;
+    }
+    if (r->chain_stage != 2) return fail(MMG_ERR_ARG, "the slice's map is gone once mmg_chain_finish has run");
+    for (int e = 0; e < J; e++) map[e] = r->chain_map[e];       // class 0: search() scans one alignment
+    if (n) *n = J;
+    return MMG_OK;
+}
+
+uint32_t mmg_chain_entry(const uint8_t *maps, int stride, int nslices) {
+    uint32_t ph = 0;                                             // the chain starts at element 0 of slice 0
+    for (int k = 0; k < nslices; k++) ph = maps[(size_t)k * stride + ph];
+    return ph;
+}
+
+int mmg_chain_finish(mmg_results *r, uint32_t entry_phase) {
+    if (!r || r->chain_stage == 0) return fail(MMG_ERR_ARG, "not a chain slice");
+    if (r->error != MMG_OK) return r->error;
+    if (r->chain_stage == 3) return fail(MMG_ERR_ARG, "mmg_chain_finish called twice");
+    if (entry_phase >= (uint32_t)r->rq.prog->dev.Jmax) return fail(MMG_ERR_ARG, "entry phase outside the pattern's jump range");
+    try {
+        if (r->chain_stage == 1) finish_chain_maps(r);
+        const MmgProgram &P = r->rq.prog->dev;
+        TiledState &t = r->t;
+        std::lock_guard<std::mutex> lock(r->dev->mu);
+        t.G.entry[0] = entry_phase;
+        r->stats.chain_entry = entry_phase;
+        t.chain = CHAIN_FULL;                                    // any later re-run does both halves
+        if (t.generation == t.ws->generation) {
+            CU(mmg_launch_chain_resolve(P, t.G, t.X, r->d_off, r->d_val, t.cap, r->stream));
+            r->launches += 2;
+            t.ws->dirty = false;
+        } else {
+            enqueue_tiled(r);                                    // another scan used the workspace in between
+        }
+        CU(cudaEventRecord(r->ev[3], r->stream));
+    } catch (const ScanError &e) {
+        r->error = e.code;
+        cudaGetLastError();
+        return e.code;
+    }
+    r->chain_stage = 3;
+    r->pending = true;
+    return MMG_OK;
 }
 
 static int engine_scan(const mmg_program *p, const void *bytes, uint64_t nbytes, int mem, uint64_t file_size,
@@ -904,6 +1052,10 @@ const uint32_t *mmg_results_device_values(const mmg_results *r) { return r ? don
 void mmg_results_free(mmg_results *r) {
     if (!r) return;
     if (r->pending) finish_scan(r);
+    if (r->chain_stage == 1 || r->chain_stage == 2) {       // abandoned chain slice: its kernels still use the buffers
+        if (r->ev[3]) cudaEventSynchronize(r->ev[3]);
+        release_inflight(r);
+    }
     // one allocation: offsets, then values.  A gather that still reads the lists on its own stream has redirected
     // the release to that stream (mmg_internal_results_free_on): the allocator then cannot recycle them early.
     if (r->d_off) cudaFreeAsync(r->d_off, r->free_stream ? r->free_stream : r->stream);

@@ -53,6 +53,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -68,10 +69,10 @@ NcclApi &nccl() {
     if (!api.lib) return api;
 #define LOAD(name) *(void **)(&api.name) = dlsym(api.lib, "nccl" #name)
     LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(GroupStart); LOAD(GroupEnd);
-    LOAD(Send); LOAD(Recv); LOAD(GetErrorString);
+    LOAD(Send); LOAD(Recv); LOAD(AllGather); LOAD(GetErrorString);
 #undef LOAD
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
-             api.Recv && api.GetErrorString;
+             api.Recv && api.AllGather && api.GetErrorString;
     return api;
 }
 
@@ -91,6 +92,7 @@ int err(int code, const std::string &msg) {
         if (e_ != cudaSuccess) return err(MMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+const int CHAIN_MAP = 128;   // bytes of a slice map on the wire (mmg_program_max_jump <= 128 entry phases)
 const int HDR = 64;      // header entries per rank (list counts); nlists <= 60
 
 }  // namespace
@@ -111,6 +113,9 @@ struct mmg_comm {
     // ranks != 0: what the last gather could not pack, copied into owned buffers, sent at the start of the next call
     struct Deferred { uint64_t *off; uint32_t *val; uint64_t n; };
     std::vector<Deferred> deferred;
+    // mmg_comm_search: the slice maps of all ranks (CHAIN_MAP bytes each); [world] is this rank's own map
+    uint8_t *chain_host = nullptr;  // pinned
+    uint8_t *chain_dev = nullptr;
 };
 
 struct mmg_gathered {
@@ -244,6 +249,8 @@ void destroy_comm(mmg_comm *c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     cudaFree(c->pack_off); cudaFree(c->pack_val); cudaFree(c->recv_off); cudaFree(c->recv_val);
     if (c->hdr_host) cudaFreeHost(c->hdr_host);
+    if (c->chain_host) cudaFreeHost(c->chain_host);
+    cudaFree(c->chain_dev);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->hdr_ready) cudaEventDestroy(c->hdr_ready);
@@ -438,6 +445,47 @@ int mmg_comm_wait(mmg_comm *c, float *ms_last) {
         *ms_last = 0.f;
         if (c->timed && cudaEventElapsedTime(ms_last, c->t0, c->t1) != cudaSuccess) { cudaGetLastError(); *ms_last = 0.f; }
     }
+    return MMG_OK;
+}
+
+// One chain over a buffer spread over the ranks: see include/mmoore_b200.h.  The all-gather of the slice maps runs on
+// the gather stream like every other NCCL call of the communicator; the host waits for it (the entry phase is needed
+// to enqueue the second half of the scan), which costs one round trip of a few dozen microseconds per search.
+int mmg_comm_search(mmg_comm *c, const mmg_program *p, const void *data, uint64_t owned_len, uint64_t avail_len,
+                    int mem, uint64_t first_element, mmg_results **out) {
+    if (!c || !p || !out) return err(MMG_ERR_ARG, "bad search arguments");
+    *out = nullptr;
+    finish_inflight(c);                                   // same entry discipline as a gather: pending receives and
+    if (int rc = flush_deferred(c); rc != MMG_OK) return rc;     // deferred sends go first, in the same order on every rank
+    const size_t M = CHAIN_MAP;
+    if (!c->chain_host) {
+        CUC(cudaHostAlloc((void **)&c->chain_host, (size_t)(c->world + 1) * M, cudaHostAllocDefault));
+        CUC(cudaMalloc((void **)&c->chain_dev, (size_t)(c->world + 1) * M));
+    }
+    mmg_results *r = nullptr;
+    int rc = mmg_chain_begin(p, data, owned_len, avail_len, mem, first_element, &r);
+    uint8_t *mine = c->chain_host + (size_t)c->world * M;
+    std::memset(mine, 0xFF, M);                           // 0xFF in entry 0 tells the others that this rank failed
+    int n = 0;
+    if (rc == MMG_OK) rc = mmg_chain_map(r, mine, (int)M, &n);
+    if (rc != MMG_OK) std::memset(mine, 0xFF, M);
+    // every rank takes part in the exchange even after a local failure, so that nobody is left waiting
+    cudaStream_t stream = c->stream;
+    auto exchange = [&]() -> int {
+        CUC(cudaMemcpyAsync(c->chain_dev + (size_t)c->world * M, mine, M, cudaMemcpyHostToDevice, stream));
+        NC(nccl().AllGather(c->chain_dev + (size_t)c->world * M, c->chain_dev, M, ncclUint8, c->comm, stream));
+        CUC(cudaMemcpyAsync(c->chain_host, c->chain_dev, (size_t)c->world * M, cudaMemcpyDeviceToHost, stream));
+        CUC(cudaStreamSynchronize(stream));
+        return MMG_OK;
+    };
+    const int xrc = exchange();
+    if (rc == MMG_OK && xrc != MMG_OK) rc = xrc;
+    if (rc == MMG_OK)
+        for (int k = 0; k < c->world; k++)
+            if (c->chain_host[(size_t)k * M] == 0xFF) { rc = err(MMG_ERR_CUDA, "the slice scan of another rank failed"); break; }
+    if (rc == MMG_OK) rc = mmg_chain_finish(r, mmg_chain_entry(c->chain_host, (int)M, c->rank));
+    if (rc != MMG_OK) { if (r) mmg_results_free(r); return rc; }
+    *out = r;
     return MMG_OK;
 }
 

@@ -10,6 +10,12 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
                               cudaStream_t stream);
 cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
                                uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
+// one block of more than 128 segments: its phase prefix runs in two levels and needs MmgScratch::rangemap (+1 launch)
+bool mmg_resolve_two_level(const MmgGeom &G);
+// slice of a longer chain (mmg_chain_*): maps of the slice first; entry phases + resolve once G.entry is known
+cudaError_t mmg_launch_chain_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream);
+cudaError_t mmg_launch_chain_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                                     uint32_t *out_val, uint64_t capacity, cudaStream_t stream);
 // sparse scans: the filter kernels resolve the engine blocks themselves when MmgScratch::fuse is set (no resolve launch);
 // host_status[4] != 0 afterwards: a block was too dense, run mmg_launch_resolve over the same event lists
 bool mmg_sparse_resolve_supported(const MmgGeom &G);

@@ -1180,6 +1180,8 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #endif
 #define RESOLVE_THREADS 128
 #define RESOLVE_FAST_J 16u
+#define RESOLVE_BATCH 16
+#define SE_STRIDE (RESOLVE_THREADS + 1)     // words per residue row of the fast maps: odd, so that the rows of one sub-tile lie in different banks
 
 template <int W, bool BE, bool MAPS_ONLY>
 __global__ void __launch_bounds__(RESOLVE_THREADS)
@@ -1194,11 +1196,14 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     // sits on residue r in front of the events seen so far:  E[r] <- E[(r + advance) mod J0] (+1 for a match).
     const bool fast = P.J0 == P.Jmax && P.Jmax <= RESOLVE_FAST_J;
     uint8_t *s_map = rs_smem;
-    uint32_t *s_E = reinterpret_cast<uint32_t *>(rs_smem);      // word = exit phase | matches << 8, index (c * 16 + r) * 128 + tid
-    uint8_t *s_ph = s_map + (fast ? (size_t)RESOLVE_THREADS * npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * npads * jp);
+    uint32_t *s_E = reinterpret_cast<uint32_t *>(rs_smem);      // word = exit phase | matches << 8, index (c * 16 + r) * SE_STRIDE + tid
+    uint8_t *s_ph = s_map + (fast ? (size_t)SE_STRIDE * npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * npads * jp);
     uint8_t *s_has = s_ph + RESOLVE_THREADS * 2;
     __shared__ uint32_t s_bi, s_cnt[RESOLVE_THREADS / 32], s_phase[2];
     __shared__ uint64_t s_before;
+    // fast maps, step (b): [warp][class * 16 + residue][k] = phase with which the chain that enters the warp's 32
+    // sub-tiles on that residue enters sub-tile k; s_wmap = where it leaves the 32 sub-tiles
+    __shared__ uint8_t s_traj[RESOLVE_THREADS / 32][32][33], s_wmap[RESOLVE_THREADS / 32][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
@@ -1212,7 +1217,9 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const uint32_t t_begin = rb * G.spb + si * RESOLVE_THREADS;
     const uint32_t t_end = G.segs_per_block == 1 ? min((rb + 1) * G.spb, G.nsub)
                                                  : min(min(t_begin + RESOLVE_THREADS, (rb + 1) * G.spb), G.nsub);
-    if (tid < 2) s_phase[tid] = (MAPS_ONLY || si == 0) ? 0u : X.segphase[bi * 2 + tid];   // the chain restarts at every engine block
+    // the chain restarts at every engine block (entry phase 0); a slice of a longer chain (mmg_chain_*) is entered with
+    // the phase the slices before it leave behind, and segment k > 0 of a block with what k_segphase / k_chainphase found
+    if (tid < 2) s_phase[tid] = MAPS_ONLY ? 0u : G.chain ? X.segphase[bi * 2 + tid] : si == 0 ? 0u : X.segphase[bi * 2 + tid];
     __syncthreads();
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
     const uint32_t magic = 65536u / J0 + 1u;      // q mod J0 = q - J0 * ((q * magic) >> 16), exact for q < 4096, J0 <= 16
@@ -1238,13 +1245,15 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         uint32_t n = 0;
         uint32_t *ev = nullptr;
         s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0;
-        if (he && fast) {
-            n = ext.y;
-            ev = X.ev + ext.x;
+        if (fast && t < t_end) {
             const uint32_t base = NP % J0;
             for (uint32_t c = 0; c < npads; c++)
                 for (uint32_t r = 0; r < J0; r++)      // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0
-                    s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] = r >= base ? r - base : r + J0 - base;
+                    s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] = r >= base ? r - base : r + J0 - base;
+        }
+        if (he && fast) {
+            n = ext.y;
+            ev = X.ev + ext.x;
             uint32_t seen = 0;
             auto step = [&](uint32_t w) {
                 const uint32_t off = MMG_EV_OFF(w);
@@ -1253,26 +1262,28 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 const uint32_t r = q - J0 * ((q * magic) >> 16);
                 uint32_t ry = r + MMG_EV_JUMP(w);       // advance <= J0
                 if (ry >= J0) ry -= J0;
-                s_E[(c * RESOLVE_FAST_J + r) * RESOLVE_THREADS + tid] =
-                    s_E[(c * RESOLVE_FAST_J + ry) * RESOLVE_THREADS + tid] + ((w >> 16) & 0x100u);
+                s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] =
+                    s_E[(c * RESOLVE_FAST_J + ry) * SE_STRIDE + tid] + ((w >> 16) & 0x100u);
                 seen |= 1u << c;
             };
-            // right to left, eight events per batch; the next batch is requested before the current one is applied, so the
-            // memory round trips of a long event list overlap with the dependent shared-memory updates
+            // right to left, RESOLVE_BATCH events per batch; the next batch is requested before the current one is
+            // applied, so the memory round trips of a long event list overlap with the dependent shared-memory updates
+            // (16 rather than 8 per batch: the round trips, not the updates, bound this step -- 78 events per sub-tile
+            // of an 8-bit text search are five round trips instead of ten)
             {
-                uint32_t cur[8], nxt[8];
+                uint32_t cur[RESOLVE_BATCH], nxt[RESOLVE_BATCH];
                 uint32_t i = n;
 #pragma unroll
-                for (int k = 0; k < 8; k++) cur[k] = (uint32_t)k < i ? ev[i - 1 - k] : 0u;
+                for (int k = 0; k < RESOLVE_BATCH; k++) cur[k] = (uint32_t)k < i ? ev[i - 1 - k] : 0u;
                 while (i > 0) {
-                    const uint32_t ni = i > 8 ? i - 8 : 0u;
+                    const uint32_t ni = i > RESOLVE_BATCH ? i - RESOLVE_BATCH : 0u;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) nxt[k] = (uint32_t)k < ni ? ev[ni - 1 - k] : 0u;
+                    for (int k = 0; k < RESOLVE_BATCH; k++) nxt[k] = (uint32_t)k < ni ? ev[ni - 1 - k] : 0u;
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
+                    for (int k = 0; k < RESOLVE_BATCH; k++)
                         if ((uint32_t)k < i) step(cur[k]);
 #pragma unroll
-                    for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+                    for (int k = 0; k < RESOLVE_BATCH; k++) cur[k] = nxt[k];
                     i = ni;
                 }
             }
@@ -1302,7 +1313,43 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             }
         }
         __syncthreads();
-        if (MAPS_ONLY) {
+        // (b, fast maps) Every sub-tile of the round has a map now, so the composition needs no bookkeeping, and it runs
+        // in two levels instead of one warp walking all 128 sub-tiles (which was a third of the kernel's run time on a
+        // dense 16 MiB input): lane (class, residue) of warp w follows its residue through sub-tiles 32w .. 32w+31 and
+        // notes the phase in front of each one; the four warp maps are then chained from the block's entry phase, which
+        // selects the trajectory that is real.
+        uint32_t fin[2] = {0u, 0u};
+        if (fast) {
+            const uint32_t c = (uint32_t)lane >> 4, r = (uint32_t)lane & 15u;
+            const bool act = c < npads && r < J0;
+            const uint32_t w0 = (uint32_t)wid * 32u;
+            const uint32_t kmax = nvalid > w0 ? min(32u, nvalid - w0) : 0u;
+            uint32_t ph = r;
+            for (uint32_t k = 0; k < kmax; k++) {
+                s_traj[wid][lane][k] = (uint8_t)ph;
+                if (act) ph = s_E[(c * RESOLVE_FAST_J + ph) * SE_STRIDE + w0 + k] & 0xFFu;
+            }
+            s_wmap[wid][lane] = (uint8_t)ph;
+            __syncthreads();
+            for (uint32_t cc = 0; cc < npads; cc++) {
+                uint32_t e = MAPS_ONLY ? 0u : s_phase[cc];
+                if (!MAPS_ONLY) {
+                    for (int w = 0; w < wid; w++) e = s_wmap[w][cc * 16u + e];
+                    if ((uint32_t)tid < nvalid) s_ph[tid * 2 + cc] = s_traj[wid][cc * 16u + e][lane];
+                    for (int w = wid; w < RESOLVE_THREADS / 32; w++) e = s_wmap[w][cc * 16u + e];
+                }
+                fin[cc] = e;
+            }
+            if (MAPS_ONLY) {
+                if (tid < 32 && act) {
+                    uint32_t e = r;
+                    for (int w = 0; w < RESOLVE_THREADS / 32; w++) e = s_wmap[w][c * 16u + e];
+                    X.segmap[((size_t)bi * 2 + c) * jp + r] = (uint8_t)e;
+                }
+                return;
+            }
+        }
+        if (MAPS_ONLY) {            // (general maps)
             // (b') the map of the whole segment: lane e follows entry phase e through the sub-tile maps (a segment is
             // one round, so this is all the kernel has to produce)
             if (wid < (int)npads) {
@@ -1316,7 +1363,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                             const uint32_t l = g + __ffs(m) - 1;
                             m &= m - 1;
                             if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);
-                            ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * RESOLVE_THREADS + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
+                            ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * SE_STRIDE + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
                             done = l + 1;
                         }
                     }
@@ -1327,8 +1374,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             return;
         }
         PHASE_MARK(1);
-        // (b) phases: warp c composes the maps of class c over the sub-tiles of this round, in order
-        if (wid < (int)npads) {
+        // (b, general maps) phases: warp c composes the maps of class c over the sub-tiles of this round, in order
+        if (!fast && wid < (int)npads) {
             const uint32_t c = wid;
             uint32_t ph = s_phase[c], done = 0;
             for (uint32_t g = 0; g < RESOLVE_THREADS && g < nvalid; g += 32) {
@@ -1338,7 +1385,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     m &= m - 1;
                     if (l > done) ph = lattice_advance(ph, (l - done) * NP, J0);
                     if (lane == 0) s_ph[l * 2 + c] = (uint8_t)ph;
-                    ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * RESOLVE_THREADS + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
+                    ph = fast ? (s_E[(c * RESOLVE_FAST_J + ph) * SE_STRIDE + l] & 0xFFu) : s_map[((size_t)l * npads + c) * jp + ph];
                     done = l + 1;
                 }
             }
@@ -1346,6 +1393,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             if (lane == 0) s_phase[c] = ph;
         }
         __syncthreads();
+        if (fast && tid < 2) s_phase[tid] = fin[tid];       // (every thread has read the old value before the barrier)
         PHASE_MARK(2);
         // (c) replay the true chains through this thread's events
         uint32_t cnt = 0;
@@ -1355,7 +1403,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             for (uint32_t c = 0; c < npads; c++)
                 if (s_has[tid * 2 + c]) {
                     xc[c] = xm[c] = s_ph[tid * 2 + c];      // entry phase < J0: position and residue coincide
-                    cnt += s_E[(c * RESOLVE_FAST_J + xc[c]) * RESOLVE_THREADS + tid] >> 8;
+                    cnt += s_E[(c * RESOLVE_FAST_J + xc[c]) * SE_STRIDE + tid] >> 8;
                 }
             if (cnt) {
                 auto visit = [&](uint32_t i, uint32_t w) {
@@ -1508,7 +1556,7 @@ k_segphase(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch
     extern __shared__ __align__(16) uint8_t sp_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t rb = blockIdx.x * SEGPHASE_WARPS + wid;
-    if (rb >= G.nblocks) return;
+    if (rb >= G.nblocks || events_overflowed(X)) return;       // (overflow: no maps were written, the host re-runs the scan)
     const uint32_t row = 2u * jp;                           // bytes of one segment's maps (both classes)
     uint8_t *stage = sp_smem + (size_t)wid * 32u * row;
     const uint32_t first = rb * G.segs_per_block;
@@ -1516,6 +1564,116 @@ k_segphase(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch
     uint32_t ph = 0;                                        // lanes 0 and 1 follow classes 0 and 1
     for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
         const uint32_t ns = min(32u, nseg - s0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(X.segmap + (size_t)(first + s0) * row);
+        for (uint32_t i = lane; i < ns * row / 16u; i += 32) reinterpret_cast<uint4 *>(stage)[i] = src[i];
+        __syncwarp();
+        if (lane < (int)G.npads) {
+            for (uint32_t k = 0; k < ns; k++) {
+                X.segphase[(size_t)(first + s0 + k) * 2 + lane] = (uint8_t)ph;
+                ph = stage[k * row + lane * jp + ph];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2c: ONE chain over a buffer that is cut into slices (mmg_chain_*, one slice per GPU).  A slice is scanned before
+// its entry phase is known: the filter and the segment maps do not depend on it.  What the other slices need from
+// this one is its MAP -- exit phase for every possible entry phase -- i.e. the composition of all its segment maps.
+// 8 GiB are 16384 segments, so the composition runs in two levels:
+//   k_rangemap   warp j composes the segments of range j (<= 128 ranges), lane = entry phase, 32 segments staged in
+//                shared memory at a time (as in k_segphase)
+//   k_slicemap   one CTA composes the range maps (thread = class x entry phase) into the pinned host buffer and
+//                hands the filter's event counts to the host (no resolve kernel has run yet to do that)
+// and, once the entry phase arrived (exchange between the ranks, then mmg_chain_finish):
+//   k_chainphase warp j walks the range maps 0..j-1 from the slice's entry phase, then its own segments, writing the
+//                entry phase of every segment; k_resolve follows as for any block cut into segments.
+// ------------------------------------------------------------------------------------------
+
+#define CHAIN_RANGES 128
+#define CHAIN_WARPS 4
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+k_rangemap(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X, uint32_t jp, uint32_t Jmax,
+           uint32_t nsegs, uint32_t per_range, uint32_t nranges) {
+    extern __shared__ __align__(16) uint8_t cr_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x * CHAIN_WARPS + wid;
+    if (j >= nranges || events_overflowed(X)) return;          // (overflow: no maps were written, the host re-runs the scan)
+    const uint32_t row = 2u * jp;
+    uint8_t *stage = cr_smem + (size_t)wid * 32u * row;
+    const uint32_t first = j * per_range;
+    const uint32_t ns_all = min(per_range, nsegs - first);
+    uint32_t ph[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) ph[c][g] = (uint32_t)(g * 32 + lane);
+    for (uint32_t s0 = 0; s0 < ns_all; s0 += 32) {
+        const uint32_t ns = min(32u, ns_all - s0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(X.segmap + (size_t)(first + s0) * row);
+        for (uint32_t i = lane; i < ns * row / 16u; i += 32) reinterpret_cast<uint4 *>(stage)[i] = src[i];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                if (c < (int)G.npads && (uint32_t)(g * 32 + lane) < Jmax)
+                    for (uint32_t k = 0; k < ns; k++) ph[c][g] = stage[k * row + c * jp + ph[c][g]];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            if (c < (int)G.npads && (uint32_t)(g * 32 + lane) < Jmax)
+                X.rangemap[((size_t)j * 2 + c) * jp + g * 32 + lane] = (uint8_t)ph[c][g];
+}
+
+__global__ void __launch_bounds__(256)
+k_slicemap(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X, uint32_t jp, uint32_t Jmax, uint32_t nranges) {
+    extern __shared__ __align__(16) uint8_t cs_smem[];
+    const uint32_t row = 2u * jp;
+    for (uint32_t i = threadIdx.x; i < nranges * row / 16u; i += blockDim.x)
+        reinterpret_cast<uint4 *>(cs_smem)[i] = reinterpret_cast<const uint4 *>(X.rangemap)[i];
+    __syncthreads();
+    const uint32_t c = threadIdx.x >> 7, e = threadIdx.x & 127u;
+    if (c < G.npads && e < Jmax && !events_overflowed(X)) {
+        uint32_t ph = e;
+        for (uint32_t j = 0; j < nranges; j++) ph = cs_smem[j * row + c * jp + ph];
+        X.slicemap_host[c * jp + e] = (uint8_t)ph;
+    }
+    if (threadIdx.x == 0) {            // the overflow check of the host needs the filter's event counts now
+        X.host_status[0] = reinterpret_cast<volatile uint64_t *>(X.status)[0];
+        X.host_status[1] = reinterpret_cast<volatile uint64_t *>(X.status)[1];
+        X.host_status[2] = 0;
+        X.host_status[4] = 0;
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+k_chainphase(const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X, uint32_t jp, uint32_t nsegs,
+             uint32_t per_range, uint32_t nranges) {
+    extern __shared__ __align__(16) uint8_t cp_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t row = 2u * jp;
+    uint8_t *ranges = cp_smem;                                         // [nranges][row]
+    uint8_t *stage = cp_smem + (size_t)CHAIN_RANGES * row + (size_t)wid * 32u * row;
+    const uint32_t j = blockIdx.x * CHAIN_WARPS + wid;
+    const uint32_t jmax_cta = min(blockIdx.x * CHAIN_WARPS + CHAIN_WARPS - 1, nranges - 1);     // ranges this CTA looks back over
+    for (uint32_t i = threadIdx.x; i < jmax_cta * row / 16u; i += blockDim.x)
+        reinterpret_cast<uint4 *>(ranges)[i] = reinterpret_cast<const uint4 *>(X.rangemap)[i];
+    __syncthreads();
+    if (j >= nranges || events_overflowed(X)) return;
+    uint32_t ph = lane < 2 ? G.entry[lane] : 0u;                      // lanes 0 and 1 follow classes 0 and 1
+    if (lane < (int)G.npads)
+        for (uint32_t i = 0; i < j; i++) ph = ranges[i * row + lane * jp + ph];
+    const uint32_t first = j * per_range;
+    const uint32_t ns_all = min(per_range, nsegs - first);
+    for (uint32_t s0 = 0; s0 < ns_all; s0 += 32) {
+        const uint32_t ns = min(32u, ns_all - s0);
         const uint4 *src = reinterpret_cast<const uint4 *>(X.segmap + (size_t)(first + s0) * row);
         for (uint32_t i = lane; i < ns * row / 16u; i += 32) reinterpret_cast<uint4 *>(stage)[i] = src[i];
         __syncwarp();
@@ -1773,26 +1931,92 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
     return cudaLaunchKernel(fn, dim3(grid), dim3(MMG_FILTER_WARPS * 32), args, filter_smem(P.W, lag_bytes), stream);
 }
 
-cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
-                               uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
-    const unsigned grid = G.nseg;                    // one CTA per segment (= engine block while blocks have <= 128 sub-tiles)
+// chain slices: segments of the slice's own block (a trailing overlap sub-tile may add one more segment to the grid)
+static uint32_t chain_segments(const MmgGeom &G) { return min(G.segs_per_block, G.nseg); }
+
+template <bool MAPS_ONLY>
+static cudaError_t launch_resolve_kernel(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                                         uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    const unsigned grid = G.nseg;
     const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
     const bool fast = P.J0 == P.Jmax && (uint32_t)P.Jmax <= RESOLVE_FAST_J;
-    const size_t smem = (fast ? (size_t)RESOLVE_THREADS * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
+    const size_t smem = (fast ? (size_t)SE_STRIDE * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
                         RESOLVE_THREADS * 4;
-    if (G.segs_per_block > 1) {
-        // blocks cut into segments: segment maps, then the phase prefix along each block
-        if (P.W == 1) k_resolve<1, false, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-        else if (G.big_endian) k_resolve<2, true, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-        else k_resolve<2, false, true><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-        k_segphase<<<(G.nblocks + SEGPHASE_WARPS - 1) / SEGPHASE_WARPS, SEGPHASE_WARPS * 32, (size_t)SEGPHASE_WARPS * 32 * 2 * jp, stream>>>(G, X, jp);
-        cudaError_t e = cudaGetLastError();
+    if (P.W == 1) k_resolve<1, false, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else if (G.big_endian) k_resolve<2, true, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else k_resolve<2, false, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    return cudaGetLastError();
+}
+
+// (the two-level phase prefix of the chain kernels also serves search() on one large buffer: a single block of
+// thousands of segments, which one warp of k_segphase would walk alone)
+static void chain_ranges(const MmgGeom &G, uint32_t &nsegs, uint32_t &per_range, uint32_t &nranges) {
+    nsegs = chain_segments(G);
+    per_range = (nsegs + CHAIN_RANGES - 1) / CHAIN_RANGES;
+    nranges = (nsegs + per_range - 1) / per_range;
+}
+
+static cudaError_t launch_chainphase(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+    uint32_t nsegs, per_range, nranges;
+    chain_ranges(G, nsegs, per_range, nranges);
+    const size_t smem = (size_t)CHAIN_RANGES * 2 * jp + (size_t)CHAIN_WARPS * 32 * 2 * jp;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_chainphase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    if (P.W == 1) k_resolve<1, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else if (G.big_endian) k_resolve<2, true, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else k_resolve<2, false, false><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    k_chainphase<<<(nranges + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, smem, stream>>>(G, X, jp, nsegs, per_range, nranges);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_rangemap(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+    uint32_t nsegs, per_range, nranges;
+    chain_ranges(G, nsegs, per_range, nranges);
+    k_rangemap<<<(nranges + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, (size_t)CHAIN_WARPS * 32 * 2 * jp, stream>>>(
+        G, X, jp, (uint32_t)P.Jmax, nsegs, per_range, nranges);
+    return cudaGetLastError();
+}
+
+bool mmg_resolve_two_level(const MmgGeom &G) { return G.nblocks == 1 && G.segs_per_block > CHAIN_RANGES; }
+
+cudaError_t mmg_launch_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                               uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    if (G.segs_per_block > 1) {
+        // blocks cut into segments: segment maps, then the phase prefix along each block
+        cudaError_t e = launch_resolve_kernel<true>(P, G, X, out_off, out_val, capacity, stream);
+        if (e != cudaSuccess) return e;
+        if (mmg_resolve_two_level(G)) {
+            e = launch_rangemap(P, G, X, stream);
+            if (e == cudaSuccess) e = launch_chainphase(P, G, X, stream);
+        } else {
+            const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+            k_segphase<<<(G.nblocks + SEGPHASE_WARPS - 1) / SEGPHASE_WARPS, SEGPHASE_WARPS * 32, (size_t)SEGPHASE_WARPS * 32 * 2 * jp, stream>>>(G, X, jp);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return launch_resolve_kernel<false>(P, G, X, out_off, out_val, capacity, stream);
+}
+
+// slice of a longer chain, first half: segment maps -> range maps -> the slice's map (pinned host buffer) + event counts
+cudaError_t mmg_launch_chain_maps(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, cudaStream_t stream) {
+    const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
+    uint32_t nsegs, per_range, nranges;
+    chain_ranges(G, nsegs, per_range, nranges);
+    cudaError_t e = launch_resolve_kernel<true>(P, G, X, nullptr, nullptr, 0, stream);
+    if (e == cudaSuccess) e = launch_rangemap(P, G, X, stream);
+    if (e != cudaSuccess) return e;
+    k_slicemap<<<1, 256, (size_t)nranges * 2 * jp, stream>>>(G, X, jp, (uint32_t)P.Jmax, nranges);
+    return cudaGetLastError();
+}
+
+// second half, with G.entry set: entry phase of every segment, then the resolve kernel
+cudaError_t mmg_launch_chain_resolve(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
+                                     uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
+    cudaError_t e = launch_chainphase(P, G, X, stream);
+    if (e != cudaSuccess) return e;
+    return launch_resolve_kernel<false>(P, G, X, out_off, out_val, capacity, stream);
 }
 
 bool mmg_sparse_resolve_supported(const MmgGeom &G) { return G.segs_per_block == 1 && G.spb <= 128; }

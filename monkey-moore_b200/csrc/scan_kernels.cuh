@@ -55,6 +55,10 @@ struct MmgGeom {
     // over the segment maps (k_segmaps, k_segphase)
     uint32_t segs_per_block;
     uint32_t nseg;         // total segments = CTAs of the resolve kernel
+    // slice of a longer chain (mmg_chain_*): the one block of the scan is entered with these phases (per alignment class)
+    // instead of 0, and every segment -- the first one too -- reads its entry phase from segphase (k_chainphase)
+    uint32_t chain;
+    uint32_t entry[2];
 };
 
 struct MmgScratch {
@@ -83,6 +87,8 @@ struct MmgScratch {
     uint64_t *host_status; // pinned, device-visible: receives status[0..3] (+ [4] = ticket[2]) when the resolve kernel ends
     uint8_t *segmap;       // [nseg][2][jp] entry phase -> exit phase of a whole segment (only when segs_per_block > 1)
     uint8_t *segphase;     // [nseg][2] entry phase of the segment
+    uint8_t *rangemap;     // [<= 128][2][jp] chain slices: composed maps of ranges of segments
+    uint8_t *slicemap_host; // pinned [2][jp]: the map of the whole slice
 };
 
 #endif

@@ -338,13 +338,17 @@ static int window(const mmo_pattern *p, const uint8_t *d, uint64_t s, int *jump)
     return 1;
 }
 
-int64_t mmo_search(const mmo_pattern *p, const void *data, uint64_t n,
-                   uint64_t *out_pos, uint32_t *out_vals, uint64_t cap) {
+/* The loop of MonkeyMoore<Ty>::search (src/core/monkey_moore.cpp:331-408, :437-544) entered at element `start`
+ * and left as soon as the chain reaches element `owned` (or runs out of data): mmo_search is the case
+ * start = 0, owned = n.  Slices of ONE chain are what the sliced / multi-GPU search hands from GPU to GPU;
+ * *exit_pos receives the position the chain left with.  Positions are relative to data[0]. */
+int64_t mmo_search_slice(const mmo_pattern *p, const void *data, uint64_t n, uint64_t start, uint64_t owned,
+                         uint64_t *exit_pos, uint64_t *out_pos, uint32_t *out_vals, uint64_t cap) {
     const uint8_t *d = (const uint8_t *)data;
     uint64_t L = (uint64_t)p->L;
     int64_t count = 0;
-    uint64_t s = 0;
-    while (s + L <= n) {
+    uint64_t s = start;
+    while (s < owned && s + L <= n) {
         int jump;
         if (window(p, d, s, &jump)) {
             if ((uint64_t)count < cap) {
@@ -358,7 +362,13 @@ int64_t mmo_search(const mmo_pattern *p, const void *data, uint64_t n,
         }
         s += (uint64_t)jump;
     }
+    if (exit_pos) *exit_pos = s;
     return count;
+}
+
+int64_t mmo_search(const mmo_pattern *p, const void *data, uint64_t n,
+                   uint64_t *out_pos, uint32_t *out_vals, uint64_t cap) {
+    return mmo_search_slice(p, data, n, 0, n, NULL, out_pos, out_vals, cap);
 }
 
 int mmo_table_size(const mmo_pattern *p) {

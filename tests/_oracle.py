@@ -67,6 +67,9 @@ class Oracle:
             lib.mmo_mode.argtypes = [C.c_void_p]
             lib.mmo_search.restype = C.c_int64
             lib.mmo_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u32p, C.c_uint64]
+            lib.mmo_search_slice.restype = C.c_int64
+            lib.mmo_search_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, u32p,
+                                             C.c_uint64]
             lib.mmo_table_size.argtypes = [C.c_void_p]
             lib.mmo_table.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u32p, u32p]
             lib.mmo_engine.restype = C.c_int64
@@ -122,6 +125,19 @@ class Oracle:
         self.lib().mmo_search(self.h, data.ctypes.data, data.size, pos.ctypes.data_as(u64p),
                               vals.ctypes.data_as(u32p), n)
         return pos[:n], vals[:n]
+
+    def search_slice(self, data, start, owned):
+        """The search loop entered at element ``start`` of ``data`` and left when the chain reaches element ``owned``
+        (or the data ends).  -> (positions, vals[n,2], exit position)"""
+        data = np.ascontiguousarray(data)
+        assert data.dtype == (np.uint8 if self.bits == 8 else np.uint16)
+        ex = C.c_uint64(0)
+        n = self.lib().mmo_search_slice(self.h, data.ctypes.data, data.size, int(start), int(owned), C.byref(ex), None, None, 0)
+        pos = np.zeros(max(n, 1), np.uint64)
+        vals = np.zeros((max(n, 1), 2), np.uint32)
+        self.lib().mmo_search_slice(self.h, data.ctypes.data, data.size, int(start), int(owned), C.byref(ex),
+                                    pos.ctypes.data_as(u64p), vals.ctypes.data_as(u32p), n)
+        return pos[:n], vals[:n], int(ex.value)
 
     def engine(self, file_bytes, block_size, big_endian=False, wrap32=True):
         """file_bytes: numpy uint8 image of the file.  -> (offsets, vals[n,2])"""

@@ -80,3 +80,33 @@ def test_offsets_beyond_4gib(gpu):
     exp, _ = _oracle_for(w, s).engine(host, w.block_size, wrap32=False)
     exp = exp + np.uint64(4 * GiB - w.block_size)             # ... at exactly the oracle's 64-bit offsets
     assert np.array_equal(off[off >= np.uint64(4 * GiB - w.block_size)], exp)
+
+
+@pytest.mark.parametrize("key,size", [("cfg5", 200 << 20), ("cfg2", 160 << 20)])
+def test_one_chain_over_hundreds_of_segments(gpu, key, size):
+    """MonkeyMoore<Ty>::search on ONE large buffer: a single block of several hundred 128-sub-tile segments, whose
+    phase prefix runs in two levels (k_rangemap, k_chainphase) -- in one call, and as two slices of ~200 segments
+    each through mmg_chain_* (ranges of two segments).  Equal to the oracle's chain over the whole buffer."""
+    import monkey_moore_b200.workloads as wl
+    w = wl.WORKLOADS[key].scaled(size)
+    s = w.searches[0]
+    prog = gpu.Program(w.bits, **s.pattern)
+    W = w.bits // 8
+    blob = wl.device_blob(w)
+    host = wl.host_blob(w)
+    elems = host.view(np.uint16) if W == 2 else host
+    exp, expv = _oracle_for(w, s).search(elems)
+    res = prog.search(blob)
+    off, val = res.arrays()
+    assert res.stats()["fast_path"] == 1 and res.stats()["launches"] >= 5
+    res.close()
+    assert off.tolist() == exp.tolist() and val.tolist() == expv.tolist()
+    n = len(elems)
+    parts = prog.search_sliced(blob, (n // 2) * W // 4096 * 4096 // W)
+    assert len(parts) == 2
+    soff = np.concatenate([p.arrays()[0] for p in parts])
+    sval = np.concatenate([p.arrays()[1] for p in parts])
+    for p in parts:
+        p.close()
+    assert soff.tolist() == exp.tolist() and sval.tolist() == expv.tolist()
+    assert len(exp) > (1000 if key == "cfg5" else 0)

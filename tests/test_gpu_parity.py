@@ -220,3 +220,79 @@ def test_sparse_resolve_kernel_and_its_fallback(gpu):
         if expect_handover:                               # sparse, handed over on dense data, general, sparse again
             assert kinds == [0, 1, 2, 0, 1], (kinds, counts)
             assert counts[0] >= 2, counts
+
+
+def chain_lists(parts):
+    off = np.concatenate([p.arrays()[0] for p in parts]) if parts else np.zeros(0, np.uint64)
+    val = np.concatenate([p.arrays()[1] for p in parts]) if parts else np.zeros((0, 2), np.uint32)
+    for p in parts:
+        p.close()
+    return off, val
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_chain_slices_equal_whole_search(gpu, seed):
+    """ONE chain over a buffer cut into slices (mmg_chain_begin / _map / _entry / _finish): the slices'
+    lists, concatenated, are MonkeyMoore<Ty>::search over the whole buffer -- from host and from device memory, for
+    slices of one sub-tile, of exactly one 128-sub-tile segment (a trailing overlap segment appears), of several
+    segments, and with other scans using the workspace between the two halves (the slice then re-runs itself)."""
+    import torch
+    rng = np.random.default_rng(7000 + seed)
+    hits = cases = 0
+    for it in range(10):
+        bits = int(rng.choice([8, 16]))
+        pat = random_pattern(rng, bits)
+        try:
+            o = Oracle(bits, **pat_kwargs(pat))
+        except OracleError:
+            continue
+        W = bits // 8
+        n = int(rng.choice([4096 // W * 3 + 5, 300_007, 1_200_011, 3_000_000]))
+        data = random_data(rng, bits, n, pat)
+        want_pos, want_val = o.search(data)
+        prog = gpu.Program(bits, **pat_kwargs(pat))
+        dev = torch.from_numpy(data.view(np.uint8)).cuda()
+        for sub_tiles in (1, 128, 130, 512):
+            slice_len = sub_tiles * 4096 // W
+            if slice_len * 400 < n:
+                continue                      # (hundreds of one-sub-tile slices of a large buffer: nothing new, just slow)
+            src = (dev.data_ptr(), dev.numel()) if (it + sub_tiles) % 2 else data
+            off, val = chain_lists(prog.search_sliced(src, slice_len))
+            assert off.tolist() == want_pos.tolist(), (pat, bits, n, sub_tiles)
+            assert [prog.table(int(v[0]), int(v[1])) for v in val] == [o.table(int(v[0]), int(v[1])) for v in want_val]
+            cases += 1
+        # the workspace is used by other scans between the halves
+        slice_len = 64 * 4096 // W
+        tail = prog.keyword_len - 1
+        slices = []
+        first = 0
+        while first < n:
+            owned = min(slice_len, n - first)
+            if n - (first + owned) <= tail:
+                owned = n - first
+            view = data[first:] if first + owned >= n else data[first:first + owned + tail]
+            slices.append(prog.chain_begin(view, owned, first))
+            prog.search(data[: 50_000 // W]).close()
+            first += owned
+        maps = [s.map() for s in slices]
+        assert all(len(m) == prog.max_jump for m in maps)
+        prog.engine_scan(data.view(np.uint8)[: 1 << 20], 65536).close()
+        parts = [s.finish(gpu.chain_entry(maps[:k])) for k, s in enumerate(slices)]
+        off, val = chain_lists(parts)
+        assert off.tolist() == want_pos.tolist(), (pat, bits, n, "interleaved")
+        hits += len(want_pos)
+    assert hits > 0 and cases > 0
+
+
+def test_chain_slice_argument_errors(gpu):
+    prog = gpu.Program(8, keyword="monkey")
+    data = np.zeros(10000, np.uint8)
+    with pytest.raises(gpu.MMError):
+        prog.chain_begin(data, 5000, 0)                  # continued slice that does not own a multiple of 4096 bytes
+    with pytest.raises(gpu.MMError):
+        prog.chain_begin(data[:4098], 4096, 0)           # continued, but fewer than keyword_len - 1 elements behind it
+    s = prog.chain_begin(data[:8192 + 5], 8192, 0)
+    s.close()                                            # abandoned before its map was read
+    s = prog.chain_begin(data, 10000, 0)
+    with pytest.raises(gpu.MMError):
+        s.finish(200)                                    # entry phase outside the jump range

@@ -2,7 +2,8 @@
 the library gathers the match lists to rank 0 over NCCL, and the result equals the one-GPU scan and the
 oracle -- for a sparse workload, for a dense one that overflows the packed buffer (spill path), and for a
 dense one with more than 10^7 matches whose lists are released right after the gather call (the library
-must keep them alive behind its own sends) while a collective of ANOTHER communicator follows at once."""
+must keep them alive behind its own sends) while a collective of ANOTHER communicator follows at once.
+Also: MonkeyMoore<Ty>::search as ONE chain over a buffer spread over the ranks (mmg_comm_search)."""
 import dataclasses
 import os
 import socket
@@ -63,6 +64,28 @@ def _worker(rank, world, port, q):
                 ok[key + ":" + s.name] = (off.tolist() == exp.tolist() and val.tolist() == expv.tolist()
                                           and o1.tolist() == exp.tolist(), len(exp))
 
+    # ---- ONE chain over the whole buffer (MonkeyMoore<Ty>::search), slices spread over the ranks: the slice maps are
+    # exchanged (all-gather of 128 bytes per rank), every rank finishes with its composed entry phase
+    for key, size in (("cfg5", 8 << 20), ("cfg2", 32 << 20), ("cfg1", 16 << 20)):
+        w = wl.WORKLOADS[key].scaled(size)
+        s = w.searches[0]
+        prog = mm.Program(w.bits, **s.pattern)
+        W = w.bits // 8
+        n = w.size // W
+        per = (n // world) * W // 4096 * 4096 // W
+        first = rank * per
+        owned = per if rank < world - 1 else n - first
+        avail = owned if rank == world - 1 else owned + prog.keyword_len - 1
+        blob = wl.device_blob(w, first_byte=first * W, nbytes=avail * W, total_size=w.size)
+        res = comm.search(prog, blob, owned, first)
+        got = comm.gather([res], fetch=True)
+        res.close()
+        if rank == 0:
+            whole = wl.host_blob(w)
+            exp, expv = oracle_of(w, s).search(whole.view(np.uint16) if W == 2 else whole)
+            off, val = got[0]
+            ok["chain:" + key] = (off.tolist() == exp.tolist() and val.tolist() == expv.tolist(), len(exp))
+
     # ---- dense case, > 10^7 matches: 4-symbol alphabet, lists freed immediately, two gathers back to back, then a
     # collective of torch's communicator while this rank's spill sends may still be in flight
     w = dataclasses.replace(wl.WORKLOADS["cfg5"], size=768 << 20, byte_mask=0x03)
@@ -120,3 +143,4 @@ def test_sharded_scan_and_nccl_gather():
     assert res and all(good for good, _ in res.values()), res
     assert res["cfg5:8bit-abc-dense"][1] > 1000      # dense enough to exercise the spill path
     assert res["dense4:8bit-abc-dense"][1] > 10_000_000
+    assert res["chain:cfg5"][1] > 1000 and res["chain:cfg2"][1] > 0
