@@ -203,7 +203,11 @@ void copy_host_to_device(uint8_t *dst, const void *src, uint64_t nbytes, cudaStr
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     StagingRing &ring = StagingRing::get();
-    if (!pinned && nbytes >= (4u << 20)) {
+    // Pageable input: above this size the bytes go through the pinned ring (pool copies overlap the H2D copies, 41 GB/s
+    // at 256 MiB); below it the driver's own staging is faster -- the ring's worker wake-ups cost more than they save
+    // (8 MiB: 0.50 ms direct against 0.9-1.4 ms through the ring, profiles/r2_bench_search_gpu.txt vs r1).
+    static const uint64_t stage_min = (getenv("MMG_STAGE_MIN_MIB") ? (uint64_t)atoi(getenv("MMG_STAGE_MIN_MIB")) : 32) << 20;
+    if (!pinned && nbytes >= stage_min) {
         std::lock_guard<std::mutex> lock(ring.mu);
         if (ring.init()) {
             static const bool prof = getenv("MMG_PROFILE_COPY") != nullptr;      // development aid: phase times on stderr
@@ -522,6 +526,9 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     G.data = rq.d_bytes; G.S = rq.S; G.base_offset = rq.base_offset;
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * W; G.npads = rq.npads;
     G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
+    // input stream marked evict_first in the L2 (MMG_L2_HINT=0 switches it off): +2 % at 512 MiB, more on larger inputs
+    static const uint32_t l2_hint = getenv("MMG_L2_HINT") ? (uint32_t)atoi(getenv("MMG_L2_HINT")) : 1u;
+    G.l2_hint = l2_hint;
     // (a chain slice that is continued by another one owns exactly B bytes of windows; the bytes behind are overlap)
     const bool continued = rq.chain && rq.S > rq.B;
     if (rq.nblocks == 1 && !continued) G.B = ((std::max<uint64_t>(std::max(rq.S, rq.B), 1) + MMG_SUBTILE - 1) / MMG_SUBTILE) * MMG_SUBTILE;

@@ -299,18 +299,27 @@ struct WarpState {
     uint32_t open_t;       // sub-tile whose event list is being filled
     uint32_t open_start;   // event index where that list starts
     uint32_t cursor;       // next free event index of this warp's private region (unclamped)
+    // extent words {first event, number of events} of the chunk's sub-tiles, lane k holding the one of sub-tile t0 + k:
+    // they leave the warp in ONE coalesced store when the chunk is done (flush_extents) instead of one 8-byte store
+    // per sub-tile as they close.
+    uint32_t t0, ex, ey;
 };
 
 __device__ __forceinline__ WarpState close_until(const MmgScratch &X, WarpState st, uint32_t t, int lane) {
-    // every sub-tile the warp passes gets its extent word {first event, number of events} -- a count of 0 where it has
-    // none, so the resolve kernels read the extents without any zeroing by the host
+    // every sub-tile the warp passes gets its extent word -- a count of 0 where it has no events, so the resolve kernels
+    // read the extents without any zeroing by the host
     if (st.open_t < t) {
-        if (lane == 0) X.ext[st.open_t] = make_uint2(st.open_start, st.cursor - st.open_start);
-        for (uint32_t u = st.open_t + 1 + (uint32_t)lane; u < t; u += 32) X.ext[u] = make_uint2(0u, 0u);      // passed without events
+        const uint32_t k = st.open_t - st.t0, ke = t - st.t0;
+        if ((uint32_t)lane == k) { st.ex = st.open_start; st.ey = st.cursor - st.open_start; }
+        else if ((uint32_t)lane > k && (uint32_t)lane < ke) { st.ex = 0u; st.ey = 0u; }      // passed without events
         st.open_start = st.cursor;
         st.open_t = t;
     }
     return st;
+}
+
+__device__ __forceinline__ void flush_extents(const MmgScratch &X, const WarpState &st, uint32_t t1, int lane) {
+    if ((uint32_t)lane < t1 - st.t0) X.ext[st.t0 + lane] = make_uint2(st.ex, st.ey);
 }
 
 // The filter kernel keeps the part of the pattern program that exact evaluation needs in shared memory
@@ -388,7 +397,11 @@ __device__ __forceinline__ uint32_t eval_window_s(const uint8_t *w) {
     return 0x100u | (uint32_t)g_sprog.match_jump;
 }
 
-// per-chunk constants of the exact-evaluation path (kept in registers / local memory of the warp)
+// per-chunk constants of the exact-evaluation path.  eval_batch is a real call (not inlined), so a ChunkCtx handed to
+// it by reference has to live in memory: as a local variable that meant nine 8-byte local-memory stores per THREAD and
+// chunk -- 2.3 KB per warp and chunk, 38 MB per 512 MiB scanned, which the input streaming through the L2 kept pushing
+// out to DRAM (the "unexplained" 34 MB of DRAM writes of round 1; profiles/r2_dram_writes.txt).  The warp's copy now
+// sits in shared memory, written once per chunk by one lane.
 struct ChunkCtx {
     int64_t s_lo, s_hi;      // window starts owned by this chunk
     int64_t q_base;          // queue entries are (window start - q_base)
@@ -402,6 +415,9 @@ struct ChunkCtx {
 
 // Exact evaluation of up to 32 queued candidate windows (one per lane, ascending window start)
 // and ordered append of the resulting events to the warp's private event region.
+#define MMG_FILTER_WARPS 8
+__shared__ ChunkCtx g_ctx[MMG_FILTER_WARPS];
+
 template <int W, bool BE>
 __device__ __noinline__ WarpState eval_batch(const MmgScratch &X, WarpState st, const ChunkCtx &C, uint32_t entry, bool have,
                                              int lane) {
@@ -461,9 +477,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// policy != 0: the lines of this copy are the first to leave the L2 again (createpolicy evict_first).  The input is
+// read exactly once; without the hint it pushes everything else out of the 126 MB L2 as it streams through -- the
+// event lists and extent words the resolve kernel is about to read, and dirty lines that then cost DRAM writes.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    if (policy)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_stream_policy(uint32_t hint) {
+    uint64_t p = 0;
+    if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 #ifndef MMG_STAGE_BYTES
@@ -478,21 +507,20 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 #endif
 #define MMG_QUEUE_CAP 320u                          // < 32 carried + <= 256 new candidates per half row (u16 entries)
 #define MMG_WARP_SMEM ((MMG_NSTAGES * MMG_STAGE_STRIDE + MMG_QUEUE_CAP * 2u + MMG_NSTAGES * 8u + 15u) & ~15u)
-#define MMG_FILTER_WARPS 8
 
 // Stage `k` of a chunk holds the slice bytes [p0 + k*2048 - 16, p0 + (k+1)*2048), clipped to
 // [0, copy_end) where copy_end is the 16-byte-aligned end of what the chunk needs; an unaligned tail
 // of the slice (< 16 bytes) is patched in by the lanes.  All positions are relative to p0 (32 bit).
 template <uint32_t STAGE = MMG_STAGE_BYTES>
 __device__ __forceinline__ void issue_stage(const uint8_t *chunk_base, bool at_slice_start, uint32_t rel_stage,
-                                            uint32_t copy_end_rel, uint32_t dst, uint32_t bar) {
+                                            uint32_t copy_end_rel, uint32_t dst, uint32_t bar, uint64_t policy) {
     uint32_t skip = 0, lo = rel_stage - 16u;          // rel_stage == 0 && at_slice_start: no left halo exists
     if (rel_stage == 0 && at_slice_start) { skip = 16u; lo = 0; }
     const uint32_t hi = min(rel_stage + STAGE, copy_end_rel);
     if ((int32_t)(hi - lo) > 0) {
         const uint32_t bytes = hi - lo;
         mbar_expect_tx(bar, bytes);
-        tma_load_1d(dst + skip, chunk_base + (int32_t)lo, bytes, bar);
+        tma_load_1d(dst + skip, chunk_base + (int32_t)lo, bytes, bar, policy);
     } else {
         mbar_arrive(bar);
     }
@@ -540,7 +568,7 @@ __device__ __noinline__ uint32_t eval_window_lds8(uint32_t wa, uint32_t sp, int 
 
 // record the extent of sub-tile t's event list: [st.open_start, cut)
 __device__ __forceinline__ WarpState close_at(const MmgScratch &X, WarpState st, uint32_t t, uint32_t cut, int lane) {
-    if (lane == 0) X.ext[t] = make_uint2(st.open_start, cut - st.open_start);       // written for every sub-tile: nothing to zero before a scan
+    if ((uint32_t)lane == t - st.t0) { st.ex = st.open_start; st.ey = cut - st.open_start; }   // (every sub-tile gets one: nothing to zero before a scan)
     st.open_start = cut;
     st.open_t = t + 1;
     return st;
@@ -747,6 +775,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
     st.cursor = reg_lo;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
     uint32_t static_round = 0;
+    const uint64_t l2pol = l2_stream_policy(G.l2_hint);
 
     for (;;) {
         // dynamic chunk scheduling: warps draw chunks from a global counter (balances the tail).  Small inputs, where
@@ -784,6 +813,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         C.reg_hi = reg_lo + X.ev_per_warp;
         st.open_t = t0;
         st.open_start = st.cursor;
+        st.t0 = t0; st.ex = 0u; st.ey = 0u;
 
         // current-element positions p run over [p0, p_end); the window start is p - sigma (- 1 for
         // the odd 16-bit class), so the chunk needs sigma + 1 extra bytes past its own window starts
@@ -802,11 +832,14 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
         const uint8_t *chunk_base = G.data + p0;
         const bool at_start = p0 == 0;
         C.q_base = (int64_t)p0 - sigma - (W == 2 ? 1 : 0);
+        __syncwarp();                       // (eval_batch calls of the previous chunk are done with the old copy)
+        if (lane == 0) g_ctx[wib] = C;
+        __syncwarp();
         uint32_t qn = 0;
         if (lane == 0) {
             uint32_t sl = slot;
             for (uint32_t k = 0; k < nst && k < MMG_NSTAGES; k++) {
-                issue_stage(chunk_base, at_start, k * MMG_STAGE_BYTES, copy_end_rel, ring_a + sl * MMG_STAGE_STRIDE, bar_a + 8 * sl);
+                issue_stage(chunk_base, at_start, k * MMG_STAGE_BYTES, copy_end_rel, ring_a + sl * MMG_STAGE_STRIDE, bar_a + 8 * sl, l2pol);
                 sl = sl + 1 == MMG_NSTAGES ? 0 : sl + 1;
             }
         }
@@ -862,7 +895,7 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
                         __syncwarp();
                         uint32_t qh = 0;
                         while (qn - qh >= 32) {
-                            st = eval_batch<W, BE>(X, st, C, queue[qh + lane], true, lane);
+                            st = eval_batch<W, BE>(X, st, g_ctx[wib], queue[qh + lane], true, lane);
                             qh += 32;
                         }
                         if (qh) {          // move the < 32 left-overs to the front
@@ -879,12 +912,13 @@ k_filter(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G
             __syncwarp();
             if (lane == 0 && k + MMG_NSTAGES < nst)
                 issue_stage(chunk_base, at_start, rel_stage + MMG_NSTAGES * MMG_STAGE_BYTES, copy_end_rel,
-                            ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot);
+                            ring_a + slot * MMG_STAGE_STRIDE, bar_a + 8 * slot, l2pol);
             if (++slot == MMG_NSTAGES) { slot = 0; parity ^= 1u; }
         }
-        if (qn) st = eval_batch<W, BE>(X, st, C, lane < qn ? queue[lane] : 0u, lane < qn, lane);
+        if (qn) st = eval_batch<W, BE>(X, st, g_ctx[wib], lane < qn ? queue[lane] : 0u, lane < qn, lane);
         __syncwarp();
         st = close_until(X, st, t1, lane);
+        flush_extents(X, st, t1, lane);
     }
     if (lane == 0) {
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));
@@ -954,6 +988,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     uint32_t dense_left = always_dense ? 0xFFFFFFFFu : 0u;
     uint32_t slot = 0, parity = 0;    // ring slot / mbarrier phase of the next stage to consume
     uint32_t static_round = 0;
+    const uint64_t l2pol = l2_stream_policy(G.l2_hint);
 
     for (;;) {
         uint32_t chunk = 0;
@@ -974,6 +1009,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         const uint32_t chunk_bytes = (t1 - t0) << MMG_SUBTILE_SHIFT;
         st.open_t = t0;
         st.open_start = st.cursor;
+        st.t0 = t0; st.ex = 0u; st.ey = 0u;
 
         // a candidate at chunk-relative position rel (current element of comparison 0) is a valid window iff
         // sg <= rel < v_hi: the window starts inside the chunk and is complete inside the block's view
@@ -997,7 +1033,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         if (lane == 0) {
             uint32_t sl = slot;
             for (uint32_t k = 0; k < nst && k < MMG_NSTAGES8; k++) {
-                issue_stage<MMG_STAGE8>(chunk_base, at_start, k * MMG_STAGE8, copy_end_rel, ring_a + sl * MMG_STRIDE8, bar_a + 8 * sl);
+                issue_stage<MMG_STAGE8>(chunk_base, at_start, k * MMG_STAGE8, copy_end_rel, ring_a + sl * MMG_STRIDE8, bar_a + 8 * sl, l2pol);
                 sl = sl + 1 == MMG_NSTAGES8 ? 0 : sl + 1;
             }
         }
@@ -1093,7 +1129,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             __syncwarp();
             if (lane == 0 && k + MMG_NSTAGES8 < nst)
                 issue_stage<MMG_STAGE8>(chunk_base, at_start, rel_stage + MMG_NSTAGES8 * MMG_STAGE8, copy_end_rel,
-                            ring_a + slot * MMG_STRIDE8, bar_a + 8 * slot);
+                            ring_a + slot * MMG_STRIDE8, bar_a + 8 * slot, l2pol);
             if (++slot == MMG_NSTAGES8) { slot = 0; parity ^= 1u; }
             // candidate-dense data (low entropy): run the next 15 stages with the depth-2 refinement, then probe again
             if (always_dense) { }
@@ -1102,6 +1138,7 @@ k_filter8(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         }
         // the row at chunk-relative 4096 * (t1 - t0) closed the last sub-tile unless the data ended before it
         if (st.open_t < t1) st = close_at(X, st, st.open_t, st.cursor, lane);
+        flush_extents(X, st, t1, lane);
     }
     if (lane == 0) {
         atomicMax((unsigned long long *)&X.status[0], (unsigned long long)(st.cursor - reg_lo));

@@ -49,6 +49,7 @@ struct MmgGeom {
     uint32_t nsub;         // total sub-tiles (fast path)
     uint32_t chunk_subs;   // sub-tiles per warp work unit (divides spb)
     uint32_t nchunks;
+    uint32_t l2_hint;      // L2 policy of the input stream: 0 none, 1 evict_first, 2 evict_unchanged (tma_load_1d)
     uint32_t static_chunks; // != 0: warp w takes chunks w, w + warps, ... instead of drawing them (small inputs)
     // resolve geometry: one CTA per SEGMENT of at most 128 sub-tiles; a block of more than 128 sub-tiles (search() on a
     // large buffer, the GUI's 8 MiB blocks) is cut into segs_per_block segments whose entry phases come from a prefix

@@ -1,7 +1,7 @@
 """Bounded workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel of the shipped library on small
 inputs -- the reference's known-answer vectors on all code paths, the five BASELINE configurations at 1-2 MiB (list
-format, fused sparse resolve and its hand-over), the segmented path of large blocks, search() on one chain, the
-distinct-table reduction.  Results are checked against the oracle, so a sanitizer run is also a parity run.
+format, fused sparse resolve and its hand-over), the segmented path of large blocks, search() on one chain -- whole
+and in slices (mmg_chain_*) --, the distinct-table reduction.  Results are checked against the oracle, so a sanitizer run is also a parity run.
     compute-sanitizer --tool memcheck python scripts/sanitize_target.py"""
 import os
 import sys
@@ -58,4 +58,15 @@ for key, size in (("cfg1", 1 << 20), ("cfg2", 2 << 20), ("cfg3", 1 << 20), ("cfg
             assert r.offsets.tolist() == pos.tolist(), (key, s.name, "search")
         r.close()
         n += 1
+        if not s.big_endian:
+            # the same chain in slices (mmg_chain_*): one sub-tile, 64 and 128 sub-tiles (the latter adds the overlap segment)
+            W = w.bits // 8
+            for subs, view in ((1, data[: (5 * 4096 + 78) // W]), (64, data), (128, data)):
+                want = pos if view is data else o.search(view)[0]
+                parts = prog.search_sliced(view, subs * 4096 // W)
+                got = np.concatenate([p.arrays()[0] for p in parts])
+                for p in parts:
+                    p.close()
+                assert got.tolist() == want.tolist(), (key, s.name, "sliced", subs)
+                n += 1
 print("sanitize_target: %d scans, all bit-exact" % n)
