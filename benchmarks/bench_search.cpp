@@ -88,12 +88,15 @@ static void run_engine(const char *name, const std::vector<CharType> &keyword, C
 
 int main(int argc, char **argv) {
    const double budget = argc > 1 ? std::atof(argv[1]) : 0.5;      // seconds per row
-   const bool with_engine = argc > 2 && std::string(argv[2]) == "engine";
+   const bool engine_only = argc > 2 && std::string(argv[2]) == "engine-only";      // development: only the SearchEngine::run rows
+   const bool with_engine = engine_only || (argc > 2 && std::string(argv[2]) == "engine");
    const std::vector<CharType> abcde = {'a', 'b', 'c', 'd', 'e'};
    const std::vector<CharType> front = {'*', 'b', 'c', 'd', 'e'}, middle = {'a', 'b', '*', 'd', 'e'}, end = {'a', 'b', 'c', 'd', '*'};
    // ->RangeMultiplier(4)->Range(128<<10, 16<<20): Google Benchmark appends the upper bound, so the rows are
    // 128 KiB, 512 KiB, 2 MiB, 8 MiB and 16 MiB (benchmarks/bench_search.cpp:67-105 of the reference)
+   const std::vector<CharType> monkey = {'m', 'o', 'n', 'k', 'e', 'y'}, mokeys = {'m', 'o', '*', 'k', 'e', 'y', '*', 's'};
    const size_t sizes[] = {128u << 10, 512u << 10, 2u << 20, 8u << 20, 16u << 20};
+   if (!engine_only) {
    for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/8-Bit", abcde, 0, bytes, budget);
    for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/16-Bit", abcde, 0, bytes, budget);
    for (size_t bytes : sizes) run_search<uint8_t>("BM_Search/Relative/Wildcard/Front/8-Bit", front, '*', bytes, budget);
@@ -103,9 +106,9 @@ int main(int argc, char **argv) {
    for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/Wildcard/Middle/16-Bit", middle, '*', bytes, budget);
    for (size_t bytes : sizes) run_search<uint16_t>("BM_Search/Relative/Wildcard/Back/16-Bit", end, '*', bytes, budget);
    // the BASELINE configs' own patterns (not part of the reference harness)
-   const std::vector<CharType> monkey = {'m', 'o', 'n', 'k', 'e', 'y'}, mokeys = {'m', 'o', '*', 'k', 'e', 'y', '*', 's'};
    run_search<uint8_t>("cfg1 8-bit monkey", monkey, 0, 16u << 20, budget);
    run_search<uint16_t>("cfg2 16-bit mo*key*s", mokeys, '*', 16u << 20, budget);
+   }
    if (with_engine) {
       const char *shm = "/dev/shm";
       run_engine<uint8_t>("SearchEngine::run 8-bit monkey", monkey, 0, 512u << 20, 524288, shm);

@@ -113,7 +113,8 @@ StagingPool &staging_pool() {
    return *pool;
 }
 
-constexpr uint64_t kSlabBytes = 32ull << 20;    // bytes of whole blocks handed to one GPU scan
+// bytes of whole blocks handed to one GPU scan (MMOORE_SLAB_MIB: development aid)
+static const uint64_t kSlabBytes = (std::getenv("MMOORE_SLAB_MIB") ? std::max(1, std::atoi(std::getenv("MMOORE_SLAB_MIB"))) : 32) * (1ull << 20);
 constexpr uint64_t kReadPiece = 2ull << 20;     // smallest piece one reader thread takes
 
 // Reads file bytes [lo, lo + len) into dst with several threads (pread on one descriptor); bytes the file no longer
@@ -143,6 +144,7 @@ void read_range(int fd, uint64_t lo, uint64_t len, uint8_t *dst) {
 struct PhaseClock {
    bool on = std::getenv("MMOORE_PROFILE") != nullptr;
    double t[4] = {0, 0, 0, 0};
+   double born = now();
    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
    template <class F> auto time(int k, F &&f) {
       if (!on) return f();
@@ -151,8 +153,8 @@ struct PhaseClock {
       return f();
    }
    ~PhaseClock() {
-      if (on) std::fprintf(stderr, "[mmoore] run(): take/pin %.2f ms  read %.2f ms  enqueue %.2f ms  collect %.2f ms\n",
-                           1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3]);
+      if (on) std::fprintf(stderr, "[mmoore] run(): take/pin %.2f ms  read %.2f ms  enqueue %.2f ms  collect %.2f ms  (slab loop %.2f ms)\n",
+                           1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3], 1e3 * (now() - born));
    }
 };
 
@@ -176,7 +178,19 @@ struct FileMapping {
       base = static_cast<const uint8_t *>(p);
       size = n;
    }
-   ~FileMapping() { if (base) ::munmap(const_cast<uint8_t *>(base), size); }
+   // Tearing down the page tables of a large mapping takes milliseconds (512 MiB: ~2 ms) and nobody waits for it:
+   // a detached thread does it while run() returns its results.
+   ~FileMapping() {
+      if (!base) return;
+      void *p = const_cast<uint8_t *>(base);
+      const uint64_t n = size;
+      if (n < (64ull << 20)) { ::munmap(p, n); return; }
+      try {
+         std::thread([p, n] { ::munmap(p, n); }).detach();
+      } catch (...) {
+         ::munmap(p, n);
+      }
+   }
    // the file must still be as long as when it was mapped (touching pages past a truncation would fault)
    bool intact(int fd) const {
       struct stat st;

@@ -129,7 +129,7 @@ class CopyPool {
  public:
     static CopyPool &get() { static CopyPool *p = new CopyPool(); return *p; }      // never destroyed: no thread joins at exit
     void copy(void *dst, const void *src, size_t n) {
-        const size_t piece_min = 1u << 20;
+        const size_t piece_min = 512u << 10;
         const size_t parts = std::min<size_t>(workers_.size() + 1, (n + piece_min - 1) / piece_min);
         if (parts <= 1) { std::memcpy(dst, src, n); return; }
         const size_t step = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
@@ -153,7 +153,8 @@ class CopyPool {
     struct Task { char *dst; const char *src; size_t n; Batch *batch; };
     CopyPool() {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned n = hw <= 2 ? 0u : std::min(hw - 1, 11u);
+        unsigned n = hw <= 2 ? 0u : std::min(hw - 1, 11u);
+        if (const char *e = getenv("MMG_COPY_THREADS")) n = (unsigned)std::max(0, atoi(e) - 1);       // development aid
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); }).detach();
     }
     void run() {
@@ -180,7 +181,7 @@ class CopyPool {
 // H2D copy each), so the link runs at its own speed instead of the driver's single-threaded pageable path.
 struct StagingRing {
     static constexpr int K = 4;
-    static constexpr size_t CHUNK = 4u << 20;
+    static constexpr size_t CHUNK = 8u << 20;      // (4 MiB chunks in 1 MiB pieces kept 4 of 12 copy threads busy: 8 GB/s, profiles/r2_stage_sweep.txt)
     std::mutex mu;                       // one staged copy at a time per process
     uint8_t *buf[K] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t done[K] = {nullptr, nullptr, nullptr, nullptr};
