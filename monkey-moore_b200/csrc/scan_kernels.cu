@@ -1220,8 +1220,13 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define RESOLVE_BATCH 16
 #define SE_STRIDE (RESOLVE_THREADS + 1)     // words per residue row of the fast maps: odd, so that the rows of one sub-tile lie in different banks
 
-template <int W, bool BE, bool MAPS_ONLY>
-__global__ void __launch_bounds__(RESOLVE_THREADS)
+// SPLIT > 1 (small inputs, where a CTA has an SM to itself and step (a) is one thread applying ~80 events at the issue
+// latency of a lone warp): SPLIT threads share the event list of a sub-tile.  Thread (sub-tile, part) applies its
+// quarter of the events to a map of its own that starts as the identity on residues (the rightmost part: as the
+// sub-tile's default exit map); the owner thread (part 0) then chains the SPLIT partial maps, exactly as step (b)
+// chains the maps of whole sub-tiles.  The helper warps leave after that.
+template <int W, bool BE, bool MAPS_ONLY, int SPLIT>
+__global__ void __launch_bounds__(RESOLVE_THREADS * SPLIT)
 k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, const __grid_constant__ MmgScratch X,
           uint64_t *out_off, uint32_t *out_val, uint64_t capacity, uint32_t jp) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -1234,17 +1239,21 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
     const bool fast = P.J0 == P.Jmax && P.Jmax <= RESOLVE_FAST_J;
     uint8_t *s_map = rs_smem;
     uint32_t *s_E = reinterpret_cast<uint32_t *>(rs_smem);      // word = exit phase | matches << 8, index (c * 16 + r) * SE_STRIDE + tid
-    uint8_t *s_ph = s_map + (fast ? (size_t)SE_STRIDE * npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * npads * jp);
+    uint8_t *s_ph = s_map + (fast ? (size_t)SE_STRIDE * npads * RESOLVE_FAST_J * 4 * SPLIT : (size_t)RESOLVE_THREADS * npads * jp);
     uint8_t *s_has = s_ph + RESOLVE_THREADS * 2;
     __shared__ uint32_t s_bi, s_cnt[RESOLVE_THREADS / 32], s_phase[2];
     __shared__ uint64_t s_before;
     // fast maps, step (b): [warp][class * 16 + residue][k] = phase with which the chain that enters the warp's 32
     // sub-tiles on that residue enters sub-tile k; s_wmap = where it leaves the 32 sub-tiles
     __shared__ uint8_t s_traj[RESOLVE_THREADS / 32][32][33], s_wmap[RESOLVE_THREADS / 32][32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ uint8_t s_seen[SPLIT][RESOLVE_THREADS];
+    // tid = sub-tile of the round this thread works for; part 0 owns it (and is all there is when SPLIT == 1)
+    const int part = SPLIT == 1 ? 0 : (int)(threadIdx.x / RESOLVE_THREADS);
+    const int tid = SPLIT == 1 ? (int)threadIdx.x : (int)(threadIdx.x % RESOLVE_THREADS), lane = tid & 31, wid = tid >> 5;
+    const uint32_t part_words = SE_STRIDE * npads * RESOLVE_FAST_J;      // one partial map array (fast maps)
 
     // blocks are taken in ticket order, so every predecessor of a block is already running (look-back is safe)
-    if (tid == 0) s_bi = MAPS_ONLY ? blockIdx.x : atomicAdd(X.ticket, 1u);
+    if (threadIdx.x == 0) s_bi = MAPS_ONLY ? blockIdx.x : atomicAdd(X.ticket, 1u);
     __syncthreads();
     const uint32_t bi = s_bi;
     PHASE_INIT;
@@ -1256,7 +1265,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                                                  : min(min(t_begin + RESOLVE_THREADS, (rb + 1) * G.spb), G.nsub);
     // the chain restarts at every engine block (entry phase 0); a slice of a longer chain (mmg_chain_*) is entered with
     // the phase the slices before it leave behind, and segment k > 0 of a block with what k_segphase / k_chainphase found
-    if (tid < 2) s_phase[tid] = MAPS_ONLY ? 0u : G.chain ? X.segphase[bi * 2 + tid] : si == 0 ? 0u : X.segphase[bi * 2 + tid];
+    if (threadIdx.x < 2) s_phase[tid] = MAPS_ONLY ? 0u : G.chain ? X.segphase[bi * 2 + tid] : si == 0 ? 0u : X.segphase[bi * 2 + tid];
     __syncthreads();
     const uint32_t J0 = P.J0, Jmax = P.Jmax, NP = MMG_SUBTILE / W;
     const uint32_t magic = 65536u / J0 + 1u;      // q mod J0 = q - J0 * ((q * magic) >> 16), exact for q < 4096, J0 <= 16
@@ -1273,7 +1282,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     X.segmap[((size_t)bi * 2 + i / Jmax) * jp + i % Jmax] = (uint8_t)lattice_advance(i % Jmax, nvalid * NP, J0);
                 return;
             }
-            if (tid == 0)
+            if (threadIdx.x == 0)       // (one thread of the CTA: with SPLIT > 1 every part has a tid 0)
                 for (uint32_t c = 0; c < npads; c++) s_phase[c] = lattice_advance(s_phase[c], nvalid * NP, J0);
             continue;
         }
@@ -1281,16 +1290,21 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         // (a) maps of this thread's sub-tile, both alignment classes
         uint32_t n = 0;
         uint32_t *ev = nullptr;
-        s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0;
+        if (part == 0) { s_has[tid * 2] = 0; s_has[tid * 2 + 1] = 0; }
+        uint32_t *const s_P = s_E + (size_t)part * part_words;       // this thread's (partial) map
         if (fast && t < t_end) {
+            // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0.  With the events shared out,
+            // only the part that applies the rightmost events starts from that; the others start as the identity.
             const uint32_t base = NP % J0;
+            const bool exit_map = part == SPLIT - 1 || !he;
             for (uint32_t c = 0; c < npads; c++)
-                for (uint32_t r = 0; r < J0; r++)      // no events: the lattice of residue r leaves the sub-tile at (r - NP) mod J0
-                    s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] = r >= base ? r - base : r + J0 - base;
+                for (uint32_t r = 0; r < J0; r++)
+                    s_P[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] = !exit_map ? r : r >= base ? r - base : r + J0 - base;
         }
         if (he && fast) {
             n = ext.y;
             ev = X.ev + ext.x;
+            const uint32_t ev_lo = SPLIT == 1 ? 0u : n * (uint32_t)part / SPLIT, ev_hi = SPLIT == 1 ? n : n * (uint32_t)(part + 1) / SPLIT;
             uint32_t seen = 0;
             auto step = [&](uint32_t w) {
                 const uint32_t off = MMG_EV_OFF(w);
@@ -1299,8 +1313,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                 const uint32_t r = q - J0 * ((q * magic) >> 16);
                 uint32_t ry = r + MMG_EV_JUMP(w);       // advance <= J0
                 if (ry >= J0) ry -= J0;
-                s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] =
-                    s_E[(c * RESOLVE_FAST_J + ry) * SE_STRIDE + tid] + ((w >> 16) & 0x100u);
+                s_P[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] =
+                    s_P[(c * RESOLVE_FAST_J + ry) * SE_STRIDE + tid] + ((w >> 16) & 0x100u);
                 seen |= 1u << c;
             };
             // right to left, RESOLVE_BATCH events per batch; the next batch is requested before the current one is
@@ -1308,14 +1322,15 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             // (16 rather than 8 per batch: the round trips, not the updates, bound this step -- 78 events per sub-tile
             // of an 8-bit text search are five round trips instead of ten)
             {
+                const uint32_t *evp = ev + ev_lo;                 // this part's events: [0, i) of evp
                 uint32_t cur[RESOLVE_BATCH], nxt[RESOLVE_BATCH];
-                uint32_t i = n;
+                uint32_t i = ev_hi - ev_lo;
 #pragma unroll
-                for (int k = 0; k < RESOLVE_BATCH; k++) cur[k] = (uint32_t)k < i ? ev[i - 1 - k] : 0u;
+                for (int k = 0; k < RESOLVE_BATCH; k++) cur[k] = (uint32_t)k < i ? evp[i - 1 - k] : 0u;
                 while (i > 0) {
                     const uint32_t ni = i > RESOLVE_BATCH ? i - RESOLVE_BATCH : 0u;
 #pragma unroll
-                    for (int k = 0; k < RESOLVE_BATCH; k++) nxt[k] = (uint32_t)k < ni ? ev[ni - 1 - k] : 0u;
+                    for (int k = 0; k < RESOLVE_BATCH; k++) nxt[k] = (uint32_t)k < ni ? evp[ni - 1 - k] : 0u;
 #pragma unroll
                     for (int k = 0; k < RESOLVE_BATCH; k++)
                         if ((uint32_t)k < i) step(cur[k]);
@@ -1324,8 +1339,9 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
                     i = ni;
                 }
             }
-            s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
-        } else if (he) {
+            if (SPLIT == 1) { s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u; }
+            else s_seen[part][tid] = (uint8_t)seen;
+        } else if (he && part == 0) {
             n = ext.y;
             ev = X.ev + ext.x;
             for (uint32_t c = 0; c < npads; c++) {
@@ -1350,6 +1366,29 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             }
         }
         __syncthreads();
+        if (SPLIT > 1) {
+            // the owner chains the partial maps of its sub-tile, left to right: residue -> residue -> ... -> exit phase,
+            // matches added up (in place: entry r of the result depends on entry r of part 0 only)
+            if (part == 0 && he && fast) {
+                for (uint32_t c = 0; c < npads; c++)
+                    for (uint32_t r = 0; r < J0; r++) {
+                        uint32_t v = s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid];
+                        uint32_t m = v >> 8;
+#pragma unroll
+                        for (int p = 1; p < SPLIT; p++) {
+                            v = s_E[(size_t)p * part_words + (c * RESOLVE_FAST_J + (v & 0xFFu)) * SE_STRIDE + tid];
+                            m += v >> 8;
+                        }
+                        s_E[(c * RESOLVE_FAST_J + r) * SE_STRIDE + tid] = (v & 0xFFu) | (m << 8);
+                    }
+                uint32_t seen = 0;
+#pragma unroll
+                for (int p = 0; p < SPLIT; p++) seen |= s_seen[p][tid];
+                s_has[tid * 2] = seen & 1u; s_has[tid * 2 + 1] = (seen >> 1) & 1u;
+            }
+            __syncthreads();
+            if (part != 0) return;          // the helper warps are done (whole warps: the barriers below count the rest)
+        }
         // (b, fast maps) Every sub-tile of the round has a map now, so the composition needs no bookkeeping, and it runs
         // in two levels instead of one warp walking all 128 sub-tiles (which was a third of the kernel's run time on a
         // dense 16 MiB input): lane (class, residue) of warp w follows its residue through sub-tiles 32w .. 32w+31 and
@@ -1489,6 +1528,7 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         __syncthreads();
     }
 
+    if (SPLIT > 1 && part != 0) return;
     if (MAPS_ONLY) return;       // (an overflowed event buffer skips the loop: nothing to do, the resolve kernel reports it)
 
     PHASE_MARK(3);
@@ -1971,17 +2011,24 @@ cudaError_t mmg_launch_filter(const MmgProgram &P, const MmgGeom &G, const MmgSc
 // chain slices: segments of the slice's own block (a trailing overlap sub-tile may add one more segment to the grid)
 static uint32_t chain_segments(const MmgGeom &G) { return min(G.segs_per_block, G.nseg); }
 
+#define RESOLVE_SPLIT 4
+#define RESOLVE_SPLIT_MAX_CTAS 592u     // up to four CTAs per SM: beyond that the SMs are busy without the helper warps
+
 template <bool MAPS_ONLY>
 static cudaError_t launch_resolve_kernel(const MmgProgram &P, const MmgGeom &G, const MmgScratch &X, uint64_t *out_off,
                                          uint32_t *out_val, uint64_t capacity, cudaStream_t stream) {
     const unsigned grid = G.nseg;
     const uint32_t jp = (uint32_t)((P.Jmax + 15) / 16 * 16);
     const bool fast = P.J0 == P.Jmax && (uint32_t)P.Jmax <= RESOLVE_FAST_J;
-    const size_t smem = (fast ? (size_t)SE_STRIDE * G.npads * RESOLVE_FAST_J * 4 : (size_t)RESOLVE_THREADS * G.npads * jp) +
-                        RESOLVE_THREADS * 4;
-    if (P.W == 1) k_resolve<1, false, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else if (G.big_endian) k_resolve<2, true, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
-    else k_resolve<2, false, MAPS_ONLY><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    static const bool nosplit = getenv("MMG_NO_RESOLVE_SPLIT") != nullptr;
+    const bool one_round = G.segs_per_block > 1 || G.spb <= RESOLVE_THREADS;       // (always, but for the MMG_NOSEG debug switch)
+    const bool split = fast && P.W == 1 && grid <= RESOLVE_SPLIT_MAX_CTAS && one_round && !nosplit;
+    const size_t smem = (fast ? (size_t)SE_STRIDE * G.npads * RESOLVE_FAST_J * 4 * (split ? RESOLVE_SPLIT : 1)
+                              : (size_t)RESOLVE_THREADS * G.npads * jp) + RESOLVE_THREADS * 4;
+    if (split) k_resolve<1, false, MAPS_ONLY, RESOLVE_SPLIT><<<grid, RESOLVE_THREADS * RESOLVE_SPLIT, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else if (P.W == 1) k_resolve<1, false, MAPS_ONLY, 1><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else if (G.big_endian) k_resolve<2, true, MAPS_ONLY, 1><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
+    else k_resolve<2, false, MAPS_ONLY, 1><<<grid, RESOLVE_THREADS, smem, stream>>>(P, G, X, out_off, out_val, capacity, jp);
     return cudaGetLastError();
 }
 
