@@ -53,7 +53,7 @@ struct MmgGeom {
     uint32_t static_chunks; // != 0: warp w takes chunks w, w + warps, ... instead of drawing them (small inputs)
     // resolve geometry: one CTA per SEGMENT of at most 128 sub-tiles; a block of more than 128 sub-tiles (search() on a
     // large buffer, the GUI's 8 MiB blocks) is cut into segs_per_block segments whose entry phases come from a prefix
-    // over the segment maps (k_segmaps, k_segphase)
+    // over the segment maps (k_resolve<MAPS_ONLY>, then k_segphase or -- one block of many segments -- k_rangemap + k_chainphase)
     uint32_t segs_per_block;
     uint32_t nseg;         // total segments = CTAs of the resolve kernel
     // slice of a longer chain (mmg_chain_*): the one block of the scan is entered with these phases (per alignment class)
