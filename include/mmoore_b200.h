@@ -229,6 +229,13 @@ int mmg_synth_fill(void *device_ptr, uint64_t nbytes, uint64_t seed, uint64_t fi
  * filter kernel (sparse scans then run the separate resolve kernel like dense ones). */
 int mmg_set_path_override(int mode);
 
+/* Opt-in SUPERSET of the reference's result (not the parity target): with on != 0 every later scan of
+ * the process reports EVERY window that matches -- per block and alignment, ascending -- instead of only the matches
+ * the reference's skip chain happens to visit (src/core/monkey_moore.cpp:398-404, :526-541: after a miss the chain
+ * advances by a table value and may jump over a true match).  The filter evaluates all windows anyway; only the
+ * replay of the chain is skipped.  Returns the previous setting.  Default: off (bit-exact with the reference). */
+int mmg_set_complete_matches(int on);
+
 #ifdef __cplusplus
 }
 #endif

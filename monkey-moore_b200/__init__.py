@@ -37,6 +37,7 @@ C_ABI_SYMBOLS = [
     "mmg_comm_unique_id", "mmg_comm_create", "mmg_comm_destroy", "mmg_comm_gather", "mmg_comm_wait",
     "mmg_gathered_count", "mmg_gathered_copy", "mmg_gathered_pieces", "mmg_gathered_free",
     "mmg_chain_begin", "mmg_chain_map", "mmg_chain_entry", "mmg_chain_finish", "mmg_program_max_jump", "mmg_comm_search",
+    "mmg_set_complete_matches",
 ]
 
 _u32p = C.POINTER(C.c_uint32)
@@ -148,6 +149,12 @@ def _u32(a):
 
 def set_path_override(mode):
     return lib().mmg_set_path_override(int(mode))
+
+
+def set_complete_matches(on):
+    """Opt-in superset of the reference's result: report every matching window, not only those its skip chain visits
+    (``mmg_set_complete_matches``).  Returns the previous setting."""
+    return bool(lib().mmg_set_complete_matches(int(bool(on))))
 
 
 def set_stream(cuda_stream_handle, use_it=True):

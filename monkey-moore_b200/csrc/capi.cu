@@ -45,6 +45,7 @@ struct ScanError { int code; };
 
 std::atomic<int> g_live_comms{0};   // result-gather communicators alive in this process (comm.cu)
 int g_path_override = 0;   // 0 auto, 1 force generic, 2 force evaluate-everything tiles (testing)
+std::atomic<int> g_complete{0};   // mmg_set_complete_matches: report every matching window, not only the chain's
 thread_local cudaStream_t g_user_stream = nullptr;   // set by mmg_set_stream: scans run on the caller's stream
 thread_local bool g_use_user_stream = false;
 
@@ -383,6 +384,7 @@ void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_r
     G.data = rq.d_bytes; G.S = rq.S; G.B = rq.B; G.base_offset = rq.base_offset;
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * P.W; G.npads = rq.npads;
     G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
+    G.complete = g_complete.load() ? 1u : 0u;
     const uint64_t chains = rq.nblocks * rq.npads;
     if (chains > 0x7FFFFFFFull) throw ScanError{fail(MMG_ERR_ARG, "too many blocks for the generic path")};
     const uint32_t n = (uint32_t)chains;
@@ -487,7 +489,7 @@ void enqueue_tiled(mmg_results *res) {
         // Not beside a result gather: the fused kernel is launched cooperatively (its grid barrier needs every CTA
         // resident), so it cannot share the SMs with an NCCL kernel the way the plain persistent grid does -- scans and
         // gathers of a multi-GPU pipeline would take turns instead of overlapping.
-        t.sparse = !t.chain && !no_sparse && g_path_override != 4 && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
+        t.sparse = !t.chain && !t.G.complete && !no_sparse && g_path_override != 4 && g_live_comms.load() == 0 && hint_bytes != 0 && mmg_sparse_resolve_supported(t.G) &&
                    (double)hint_events / (double)hint_bytes * (double)t.G.B <= 128.0;       // <= 128 events per block expected
     }
     X.fuse = t.sparse ? 1u : 0u;
@@ -528,6 +530,7 @@ void launch_tiled(mmg_results *res, DeviceInfo &dev, Workspace &ws) {
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * W; G.npads = rq.npads;
     G.big_endian = rq.big_endian; G.report_shift = rq.report_shift;
     // input stream marked evict_first in the L2 (MMG_L2_HINT=0 switches it off): +2 % at 512 MiB, more on larger inputs
+    G.complete = g_complete.load() ? 1u : 0u;
     static const uint32_t l2_hint = getenv("MMG_L2_HINT") ? (uint32_t)atoi(getenv("MMG_L2_HINT")) : 1u;
     G.l2_hint = l2_hint;
     // (a chain slice that is continued by another one owns exactly B bytes of windows; the bytes behind are overlap)
@@ -788,6 +791,8 @@ int mmg_set_path_override(int mode) {
     g_path_override = mode;
     return old;
 }
+
+int mmg_set_complete_matches(int on) { return g_complete.exchange(on ? 1 : 0); }
 
 int mmg_program_create_keyword(const uint32_t *keyword, int keyword_len, uint32_t wildcard, const uint32_t *char_seq,
                                int char_seq_len, int elem_bits, mmg_program **out) {

@@ -1473,7 +1473,16 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
         PHASE_MARK(2);
         // (c) replay the true chains through this thread's events
         uint32_t cnt = 0;
-        if (he && fast) {
+        if (G.complete) {
+            // complete-match mode: every match event counts, whatever the chain does (a matching window is always an event)
+            if (he) {
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t w = ev[i];
+                    if (w & MMG_EV_MATCH) { ev[i] = w | MMG_EV_VISITED; cnt++; }
+                }
+                X.mcount[t] = cnt;
+            }
+        } else if (he && fast) {
             // the match count of the chain that really enters is already known; the replay only marks its matches
             uint32_t xc[2] = {0u, 0u}, xm[2] = {0u, 0u};
             for (uint32_t c = 0; c < npads; c++)
@@ -1870,7 +1879,7 @@ g_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
             }
             n++;
         }
-        k += r & 0xFFu;
+        k += G.complete ? 1u : (r & 0xFFu);
     }
     if (!bases) counts[chain] = n;
 }

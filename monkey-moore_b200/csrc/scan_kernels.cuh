@@ -60,6 +60,9 @@ struct MmgGeom {
     // instead of 0, and every segment -- the first one too -- reads its entry phase from segphase (k_chainphase)
     uint32_t chain;
     uint32_t entry[2];
+    // opt-in superset of the reference's result (mmg_set_complete_matches): EVERY window that matches is
+    // reported, not only those the lossy skip chain happens to visit
+    uint32_t complete;
 };
 
 struct MmgScratch {

@@ -342,6 +342,11 @@ static int window(const mmo_pattern *p, const uint8_t *d, uint64_t s, int *jump)
  * and left as soon as the chain reaches element `owned` (or runs out of data): mmo_search is the case
  * start = 0, owned = n.  Slices of ONE chain are what the sliced / multi-GPU search hands from GPU to GPU;
  * *exit_pos receives the position the chain left with.  Positions are relative to data[0]. */
+/* Opt-in complete-match mode of the product (mmg_set_complete_matches): every window is evaluated, i.e. the chain
+ * advances by 1 whatever F(s) says.  NOT reference behaviour; off by default. */
+static int g_complete = 0;
+int mmo_set_complete(int on) { int old = g_complete; g_complete = on != 0; return old; }
+
 int64_t mmo_search_slice(const mmo_pattern *p, const void *data, uint64_t n, uint64_t start, uint64_t owned,
                          uint64_t *exit_pos, uint64_t *out_pos, uint32_t *out_vals, uint64_t cap) {
     const uint8_t *d = (const uint8_t *)data;
@@ -360,7 +365,7 @@ int64_t mmo_search_slice(const mmo_pattern *p, const void *data, uint64_t n, uin
             }
             count++;
         }
-        s += (uint64_t)jump;
+        s += g_complete ? 1u : (uint64_t)jump;
     }
     if (exit_pos) *exit_pos = s;
     return count;

@@ -70,6 +70,7 @@ class Oracle:
             lib.mmo_search_slice.restype = C.c_int64
             lib.mmo_search_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, u32p,
                                              C.c_uint64]
+            lib.mmo_set_complete.argtypes = [C.c_int]
             lib.mmo_table_size.argtypes = [C.c_void_p]
             lib.mmo_table.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u32p, u32p]
             lib.mmo_engine.restype = C.c_int64
@@ -125,6 +126,11 @@ class Oracle:
         self.lib().mmo_search(self.h, data.ctypes.data, data.size, pos.ctypes.data_as(u64p),
                               vals.ctypes.data_as(u32p), n)
         return pos[:n], vals[:n]
+
+    @classmethod
+    def set_complete(cls, on):
+        """complete-match mode of the product (every window is evaluated); returns the previous setting"""
+        return bool(cls.lib().mmo_set_complete(int(bool(on))))
 
     def search_slice(self, data, start, owned):
         """The search loop entered at element ``start`` of ``data`` and left when the chain reaches element ``owned``
