@@ -30,10 +30,11 @@ extern "C" {
 #define MMG_ERR_HANG 3      /* pattern whose match advance is <= 0: the reference never terminates (:398,:526); rejected */
 #define MMG_ERR_ARG 4       /* bad argument */
 #define MMG_ERR_CUDA 5      /* CUDA runtime failure or no device (message in mmg_last_error) */
-#define MMG_ERR_TOO_LONG 6  /* keyword longer than MMG_MAX_KEYWORD */
+#define MMG_ERR_TOO_LONG 6  /* keyword longer than 32767 elements (more than 128: accepted, per-chain kernels only) */
 #define MMG_ERR_NOMEM 7
 
-#define MMG_MAX_KEYWORD 128
+#define MMG_MAX_KEYWORD 32767          /* elements; keywords of more than MMG_FAST_KEYWORD run on the per-chain kernels */
+#define MMG_FAST_KEYWORD 128
 
 typedef struct mmg_program mmg_program;   /* a compiled pattern (== one MonkeyMoore<Ty> instance) */
 typedef struct mmg_results mmg_results;   /* the match list of one scan */

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -378,8 +379,62 @@ void free_results(mmg_results *res) {
     res->d_val = nullptr;
 }
 
+// Device copies of the arrays of long keywords (MmgLongProgram), per program and device; made at the first scan (pattern
+// compilation itself needs no GPU), released by mmg_program_free.
+struct LongArrays { int device; MmgCheck *chk; int32_t *tab_key, *tab_val; };
+std::mutex g_long_mutex;
+std::multimap<const mmg_program *, LongArrays> g_long_arrays;
+
+MmgLongProgram long_program_on_device(const mmg_program *prog) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_long_mutex);
+    LongArrays a{dev, nullptr, nullptr, nullptr};
+    bool found = false;
+    auto range = g_long_arrays.equal_range(prog);
+    for (auto it = range.first; it != range.second; ++it)
+        if (it->second.device == dev) { a = it->second; found = true; }
+    if (!found) {
+        const size_t nc = prog->long_chk.size(), nt = prog->long_tab_key.size();
+        CU(cudaMalloc((void **)&a.chk, std::max<size_t>(nc, 1) * sizeof(MmgCheck)));
+        CU(cudaMalloc((void **)&a.tab_key, std::max<size_t>(nt, 1) * sizeof(int32_t)));
+        CU(cudaMalloc((void **)&a.tab_val, std::max<size_t>(nt, 1) * sizeof(int32_t)));
+        if (nc) CU(cudaMemcpy(a.chk, prog->long_chk.data(), nc * sizeof(MmgCheck), cudaMemcpyHostToDevice));
+        if (nt) {
+            CU(cudaMemcpy(a.tab_key, prog->long_tab_key.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(a.tab_val, prog->long_tab_val.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        g_long_arrays.insert({prog, a});
+    }
+    const MmgProgram &d = prog->dev;
+    MmgLongProgram P{};
+    P.W = d.W; P.L = d.L; P.modular = d.modular; P.ncheck = (int32_t)prog->long_chk.size(); P.ntab = (int32_t)prog->long_tab_key.size();
+    P.tab_default = d.tab_default; P.match_jump = d.match_jump; P.first_lit = d.first_lit; P.opp_idx = d.opp_idx;
+    P.chk = a.chk; P.tab_key = a.tab_key; P.tab_val = a.tab_val;
+    return P;
+}
+
+void release_long_program(const mmg_program *prog) {
+    std::lock_guard<std::mutex> lock(g_long_mutex);
+    auto range = g_long_arrays.equal_range(prog);
+    for (auto it = range.first; it != range.second; ++it) {
+        int cur = 0;
+        const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != it->second.device && cudaSetDevice(it->second.device) == cudaSuccess;
+        cudaFree(it->second.chk); cudaFree(it->second.tab_key); cudaFree(it->second.tab_val);
+        if (switched) cudaSetDevice(cur);
+    }
+    g_long_arrays.erase(range.first, range.second);
+    cudaGetLastError();
+}
+
 void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_results *res, uint32_t &launches) {
     const MmgProgram &P = rq.prog->dev;
+    const bool is_long = rq.prog->is_long;
+    MmgLongProgram LP{};
+    if (is_long) LP = long_program_on_device(rq.prog);
+    auto walk = [&](const MmgGeom &g, uint32_t *cnt, const uint64_t *bs, uint64_t *oo, uint32_t *ov) {
+        return is_long ? mmg_launch_generic_walk_long(LP, g, cnt, bs, oo, ov, stream) : mmg_launch_generic_walk(P, g, cnt, bs, oo, ov, stream);
+    };
     MmgGeom G{};
     G.data = rq.d_bytes; G.S = rq.S; G.B = rq.B; G.base_offset = rq.base_offset;
     G.nblocks = (uint32_t)rq.nblocks; G.ov = (uint32_t)(P.L - 1) * P.W; G.npads = rq.npads;
@@ -392,7 +447,7 @@ void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_r
     uint64_t *bases = arena.get<uint64_t>(n);
     uint64_t *bsum = arena.get<uint64_t>((n + 1023) / 1024 + 1);
     uint64_t *total_d = arena.get<uint64_t>(1);
-    CU(mmg_launch_generic_walk(P, G, counts, nullptr, nullptr, nullptr, stream));
+    CU(walk(G, counts, nullptr, nullptr, nullptr));
     CU(mmg_launch_scan(counts, n, bsum, bases, total_d, stream));
     launches += 4;
     uint64_t total = 0;
@@ -402,12 +457,12 @@ void run_generic(const ScanRequest &rq, cudaStream_t stream, Arena &arena, mmg_r
     if (total == 0) return;
     alloc_results(res, total);
     if (rq.npads == 1) {
-        CU(mmg_launch_generic_walk(P, G, counts, bases, res->d_off, res->d_val, stream));
+        CU(walk(G, counts, bases, res->d_off, res->d_val));
         launches += 1;
     } else {
         uint64_t *tmp_off = arena.get<uint64_t>(total);
         uint32_t *tmp_val = arena.get<uint32_t>(total);
-        CU(mmg_launch_generic_walk(P, G, counts, bases, tmp_off, tmp_val, stream));
+        CU(walk(G, counts, bases, tmp_off, tmp_val));
         CU(mmg_launch_generic_merge(G.nblocks, counts, bases, tmp_off, tmp_val, res->d_off, res->d_val, stream));
         launches += 2;
     }
@@ -713,7 +768,8 @@ int launch_scan(const mmg_program *prog, const void *bytes, uint64_t nbytes, int
         if (mem == MMG_MEM_HOST) CU(cudaEventRecord(res->ev[1], stream));      // end of the copy (re-recorded before the filter)
         res->rq = ScanRequest{prog, d_bytes, nbytes, B, nblocks, npads, big_endian, base_offset, report_shift, chain};
         const bool regular = nblocks == 1 || (B % MMG_SUBTILE) == 0;
-        res->tiled = regular && (g_path_override != 1 || chain);
+        if (chain && prog->is_long) throw ScanError{fail(MMG_ERR_ARG, "chain slices are not available for keywords longer than 128 elements")};
+        res->tiled = regular && (g_path_override != 1 || chain) && !prog->is_long;      // long keywords: per-chain kernels only
         res->stats.fast_path = res->tiled;
         if (chain) res->chain_map = take_map();
         if (res->tiled) {
@@ -816,7 +872,10 @@ int mmg_program_create_values(const int16_t *values, int n, int elem_bits, mmg_p
     return rc;
 }
 
-void mmg_program_free(mmg_program *p) { delete p; }
+void mmg_program_free(mmg_program *p) {
+    if (p && p->is_long) release_long_program(p);
+    delete p;
+}
 int mmg_program_keyword_len(const mmg_program *p) { return p->dev.L; }
 int mmg_program_max_jump(const mmg_program *p) { return p ? p->dev.Jmax : 0; }
 int mmg_program_mode(const mmg_program *p) { return p->mode; }

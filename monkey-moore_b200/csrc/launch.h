@@ -25,6 +25,8 @@ cudaError_t mmg_launch_emit(const MmgProgram &P, const MmgGeom &G, const MmgScra
                             uint32_t *out_val, cudaStream_t stream);
 cudaError_t mmg_launch_generic_walk(const MmgProgram &P, const MmgGeom &G, uint32_t *counts, const uint64_t *bases,
                                     uint64_t *out_off, uint32_t *out_val, cudaStream_t stream);
+cudaError_t mmg_launch_generic_walk_long(const MmgLongProgram &P, const MmgGeom &G, uint32_t *counts, const uint64_t *bases,
+                                         uint64_t *out_off, uint32_t *out_val, cudaStream_t stream);
 cudaError_t mmg_launch_generic_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases,
                                      const uint64_t *in_off, const uint32_t *in_val, uint64_t *out_off,
                                      uint32_t *out_val, cudaStream_t stream);

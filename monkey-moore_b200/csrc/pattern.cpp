@@ -47,7 +47,7 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
     *out = nullptr;
     if (elem_bits != 8 && elem_bits != 16) { err = "elem_bits must be 8 or 16"; return MMG_ERR_ARG; }
     if (keyword_len <= 0 || keyword == nullptr) { err = "empty keyword"; return MMG_ERR_EMPTY; }
-    if (keyword_len > MMG_MAXL) { err = "keyword longer than MMG_MAX_KEYWORD"; return MMG_ERR_TOO_LONG; }
+    if (keyword_len > MMG_MAXL_LONG) { err = "keyword longer than 32767 elements"; return MMG_ERR_TOO_LONG; }
     if (char_seq_len < 0 || (char_seq_len > 0 && char_seq == nullptr)) { err = "bad char_seq"; return MMG_ERR_ARG; }
 
     auto prog = new mmg_program();
@@ -160,6 +160,33 @@ int mmg_compile_pattern(const uint32_t *keyword, int keyword_len, uint32_t wildc
     d.first_lit = first_lit < L ? first_lit : 0;
     d.opp_idx = opp_idx;
     d.tab_default = std::max(skip.fallback, 1);
+    if (L > MMG_MAXL) {
+        // long keyword: the arrays go to device memory (MmgLongProgram), evaluated by the per-chain kernels only
+        prog->is_long = true;
+        for (size_t j = 0; j < skip.key.size(); j++) {
+            prog->long_tab_key.push_back(skip.key[j]);
+            prog->long_tab_val.push_back(std::max(skip.val[j], 1));
+        }
+        int first_literal = -1;
+        for (int i = 0; i < L; i++) if (literal[i]) { first_literal = i; break; }
+        int32_t jmax = match_jump;
+        for (int i = L - 1; i >= 0; i--) {
+            if (!literal[i] || i == first_literal) continue;
+            MmgCheck c;
+            c.i = static_cast<int16_t>(i);
+            c.lag = static_cast<int16_t>(i - prev[i]);
+            c.ed = ed[i];
+            c.cap = cap[i];
+            prog->long_chk.push_back(c);
+        }
+        d.ntab = 0;
+        d.ncheck = 0;
+        d.nkeys = -1;
+        d.J0 = 1;
+        d.Jmax = std::max(jmax, 1);
+        *out = guard.release();
+        return MMG_OK;
+    }
     d.ntab = static_cast<int32_t>(skip.key.size());
     int32_t max_skip = d.tab_default;
     for (int j = 0; j < d.ntab; j++) {

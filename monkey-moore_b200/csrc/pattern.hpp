@@ -30,6 +30,12 @@ struct mmg_program {
     mutable std::atomic<uint64_t> last_events{0};          // total events of the previous scan
     mutable std::atomic<uint64_t> last_bytes{0};           // bytes the previous scan covered (0: no scan yet)
 
+    // keyword longer than MMG_MAXL: dev holds the scalars only, the arrays live here (and, from the first scan on, in
+    // device memory: capi.cu uploads them per device)
+    bool is_long = false;
+    std::vector<MmgCheck> long_chk;
+    std::vector<int32_t> long_tab_key, long_tab_val;
+
     int value_of(uint32_t c) const;        // code point, or index in char_seq (0 when absent)
 };
 

@@ -53,4 +53,15 @@ struct MmgProgram {
     int32_t tab_val[MMG_MAXL];     // skip, already max(.,1)
 };
 
+// Keywords longer than MMG_MAXL (the reference accepts any length): the same program with its per-position arrays in
+// device memory instead of the kernel-parameter block.  Only the per-chain kernels (g_walk_long) run it -- one thread
+// per (block, alignment) chain, exactly the CPU's loop; correct for every length, nowhere near the streaming path's speed.
+#define MMG_MAXL_LONG 32767         // (keyword indices are int16_t in MmgCheck)
+struct MmgLongProgram {
+    int32_t W, L, modular, ncheck, ntab, tab_default, match_jump, first_lit, opp_idx;
+    const MmgCheck *chk;            // [ncheck] device
+    const int32_t *tab_key;         // [ntab] device
+    const int32_t *tab_val;
+};
+
 #endif

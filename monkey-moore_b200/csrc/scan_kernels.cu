@@ -1884,6 +1884,58 @@ g_walk(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom G, 
     if (!bases) counts[chain] = n;
 }
 
+// ---- keywords longer than MMG_MAXL: the same walk with the program's arrays in device memory (MmgLongProgram)
+template <int W, bool BE>
+__device__ __forceinline__ uint32_t eval_window_long(const MmgLongProgram &P, const uint8_t *w) {      // bit 31: match
+    const uint32_t vmask = W == 1 ? 0xFFu : 0xFFFFu;
+    for (int c = 0; c < P.ncheck; c++) {
+        const MmgCheck k = P.chk[c];
+        const int d = (int)ld_elem<W, BE>(w + (int)k.i * W) - (int)ld_elem<W, BE>(w + ((int)k.i - (int)k.lag) * W);
+        const bool pass = P.modular ? ((((uint32_t)(d - k.ed)) & vmask) == 0) : (d == k.ed);
+        if (!pass) {
+            int sk = P.tab_default;
+            for (int j = 0; j < P.ntab; j++)
+                if (P.tab_key[j] == d) sk = P.tab_val[j];
+            return (uint32_t)min(k.cap, sk);
+        }
+    }
+    return 0x80000000u | (uint32_t)P.match_jump;
+}
+
+template <int W, bool BE>
+__global__ void __launch_bounds__(128)
+g_walk_long(const __grid_constant__ MmgLongProgram P, const __grid_constant__ MmgGeom G, uint32_t *counts, const uint64_t *bases,
+            uint64_t *out_off, uint32_t *out_val) {
+    const uint64_t chain = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= (uint64_t)G.nblocks * G.npads) return;
+    const uint64_t bi = chain / G.npads, pad = chain % G.npads;
+    const uint64_t off = bi * G.B;
+    const uint64_t size = min(G.B + (uint64_t)G.ov, G.S - off);
+    uint64_t count = size / W;
+    if (pad + count * W > size) count -= 1;
+    const uint8_t *base = G.data + off + pad;
+    const uint64_t L = (uint64_t)P.L;
+    uint64_t k = 0;
+    uint32_t n = 0;
+    uint64_t at = bases ? bases[chain] : 0;
+    while (k + L <= count) {
+        const uint32_t r = eval_window_long<W, BE>(P, base + k * W);
+        if (r & 0x80000000u) {
+            if (bases) {
+                const uint64_t s = off + pad + k * W;
+                out_off[at] = (G.base_offset + s) >> G.report_shift;
+                const uint32_t v0 = ld_elem<W, BE>(G.data + s + (uint32_t)P.first_lit * W);
+                const uint32_t v1 = P.opp_idx >= 0 ? ld_elem<W, BE>(G.data + s + (uint32_t)P.opp_idx * W) : 0u;
+                out_val[at] = v0 | (v1 << 16);
+                at++;
+            }
+            n++;
+        }
+        k += G.complete ? 1u : (r & 0x7FFFFFFFu);
+    }
+    if (!bases) counts[chain] = n;
+}
+
 // two alignments of one block interleave by offset: merge them (offsets are unique)
 __global__ void __launch_bounds__(128)
 g_merge(uint32_t nblocks, const uint32_t *counts, const uint64_t *bases, const uint64_t *in_off, const uint32_t *in_val,
@@ -2141,6 +2193,16 @@ cudaError_t mmg_launch_generic_walk(const MmgProgram &P, const MmgGeom &G, uint3
     if (P.W == 1) g_walk<1, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
     else if (G.big_endian) g_walk<2, true><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
     else g_walk<2, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    return cudaGetLastError();
+}
+
+cudaError_t mmg_launch_generic_walk_long(const MmgLongProgram &P, const MmgGeom &G, uint32_t *counts, const uint64_t *bases,
+                                         uint64_t *out_off, uint32_t *out_val, cudaStream_t stream) {
+    const uint64_t chains = (uint64_t)G.nblocks * G.npads;
+    const unsigned grid = (unsigned)((chains + 127) / 128);
+    if (P.W == 1) g_walk_long<1, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    else if (G.big_endian) g_walk_long<2, true><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
+    else g_walk_long<2, false><<<grid, 128, 0, stream>>>(P, G, counts, bases, out_off, out_val);
     return cudaGetLastError();
 }
 

@@ -87,8 +87,9 @@ def test_rejects_what_the_reference_cannot_finish(mm):
         with pytest.raises(mm.MMError) as e:
             mm.Program(8, **bad)
         assert e.value.code == 3
+    assert mm.Program(8, keyword="xy" * 65).keyword_len == 130       # > 128: accepted (per-chain kernels), like the reference
     with pytest.raises(mm.MMError) as e:
-        mm.Program(8, keyword="x" * 129)
+        mm.Program(8, keyword="x" * 40000)
     assert e.value.code == 6
     with pytest.raises(mm.MMError):
         mm.Program(8, keyword="")
