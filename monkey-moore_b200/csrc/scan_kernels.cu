@@ -1319,8 +1319,8 @@ k_resolve(const __grid_constant__ MmgProgram P, const __grid_constant__ MmgGeom 
             };
             // right to left, RESOLVE_BATCH events per batch; the next batch is requested before the current one is
             // applied, so the memory round trips of a long event list overlap with the dependent shared-memory updates
-            // (16 rather than 8 per batch: the round trips, not the updates, bound this step -- 78 events per sub-tile
-            // of an 8-bit text search are five round trips instead of ten)
+            // (batches of 16 or of 8 measure the same: on small inputs the step is bound by the issue latency of a lone
+            // warp working through ~25 instructions per event, which is what SPLIT addresses, not by the round trips)
             {
                 const uint32_t *evp = ev + ev_lo;                 // this part's events: [0, i) of evp
                 uint32_t cur[RESOLVE_BATCH], nxt[RESOLVE_BATCH];
